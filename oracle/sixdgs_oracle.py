@@ -1,0 +1,469 @@
+"""CPU oracle for the 6DGS single-query pose-estimation hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package (``6dgs_b200/``) may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs do, and
+only as the checker / the CPU baseline, never as the thing measured or shipped.
+
+It is a torch-CPU (fp32) restatement of the reference algorithm written from SURVEY.md §8a, one
+function per row, each citing the reference file:line it follows.  The reference is itself pure
+torch ops on this path, so restating with the same primitive ops in the same order keeps every
+discrete decision (floor / trunc / strict ``<`` / argmax) bit-identical on CPU.
+
+Parity pin: the reference has no golden vectors of its own; this oracle is pinned
+against outputs of the UNMODIFIED reference run in the build container -- ``oracle/gen_golden.py``
+imports ``/root/reference`` through ``oracle/ref_shims.py`` and writes ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` checks every function below against those fixtures.
+
+Deliberate differences from the reference (none change results):
+  * quadricell cells are found with a per-ring monotone search instead of materialising the
+    ``[cells, 1000]`` table + ``nonzero`` + ``coalesce`` (quadricell.py:283-296) -- the table is a
+    non-decreasing cumsum so "largest index whose entry is < theta" == "count - 1";
+  * the 1000-ellipsoid cap (sampling.py:146-148) is a keyword (``max_ellipsoids``) and the
+    permutation can be injected (``ellipsoid_idx``) so capped runs are reproducible.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+TWO_PI = 2.0 * math.pi
+SURFACE_P = 1.6075
+
+# ----------------------------------------------------------------------------------------------
+# a1  scene getters -- scene/gaussian_model.py:125-158, utils/general_utils.py:103-126
+# ----------------------------------------------------------------------------------------------
+
+
+def quat_to_rotmat(rot_raw: torch.Tensor) -> torch.Tensor:
+    """(w,x,y,z) quaternion -> R.  Follows get_rotation_mat (gaussian_model.py:133-134):
+    F.normalize first (rotation_activation, :45), then build_rotation which normalises again
+    (general_utils.py:103-126)."""
+    q = torch.nn.functional.normalize(rot_raw)
+    n = torch.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2] + q[:, 3] * q[:, 3])
+    q = q / n[:, None]
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.zeros((q.shape[0], 3, 3), dtype=q.dtype)
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - w * z)
+    R[:, 0, 2] = 2 * (x * z + w * y)
+    R[:, 1, 0] = 2 * (x * y + w * z)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - w * x)
+    R[:, 2, 0] = 2 * (x * z - w * y)
+    R[:, 2, 1] = 2 * (y * z + w * x)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+# ----------------------------------------------------------------------------------------------
+# a2  degrade mask -- quadricell.py:86-97,163-188
+# ----------------------------------------------------------------------------------------------
+
+
+def _perimeter(b: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    """Ramanujan-type ellipse perimeter (quadricell.py:86-97)."""
+    s = b + c
+    num = 3 * torch.square(b - c)
+    den = 10 * s + torch.sqrt(torch.square(b) + 14 * b * c + torch.square(c))
+    return math.pi * (s + num / den)
+
+
+def _surface(a, b, c):
+    """Knud Thomsen ellipsoid surface, p = 1.6075 (quadricell.py:163-168)."""
+    acc = torch.pow(a * b, SURFACE_P) + torch.pow(a * c, SURFACE_P) + torch.pow(b * c, SURFACE_P)
+    return (4 * math.pi) * torch.pow(acc / 3, 1 / SURFACE_P)
+
+
+def ring_layout(a, b, c, target_points: int = 50):
+    """side length of the square cell and slab ("ring") count per ellipsoid
+    (quadricell.py:177-186 == :198-207)."""
+    side = torch.sqrt(_surface(a, b, c) / float(target_points))
+    rb = torch.floor(_perimeter(a, b) / (2 * side))
+    rc = torch.floor(_perimeter(a, c) / (2 * side))
+    rings = ((rb + rc) * 0.5).to(torch.long)
+    return side, rings
+
+
+def mask_degraded_ellipsoids(a, b, c, target_points: int = 50) -> torch.Tensor:
+    """valid = rings < target (quadricell.py:171-188)."""
+    _, rings = ring_layout(a, b, c, target_points)
+    return rings < target_points
+
+
+# ----------------------------------------------------------------------------------------------
+# a6  quadricell cell centres -- quadricell.py:100-160,191-319
+# ----------------------------------------------------------------------------------------------
+
+
+def quadricell_centers(a, b, c, target_points: int = 50, resolution: int = 1000, ring_chunk: int = 4096):
+    """Equal-area cell centres on every ellipsoid.
+
+    Returns (points[C,3], ellipsoid_id[C]) ordered ellipsoid-major, ring-major, cell-minor, the
+    a-axis stored in z (quadricell.py:305-319)."""
+    side, rings = ring_layout(a, b, c, target_points)
+    M = a.shape[0]
+    eid_ring = torch.repeat_interleave(torch.arange(M, dtype=torch.long), rings)
+    first_ring = torch.cumsum(rings, 0) - rings
+    ring_pos = (torch.arange(int(rings.sum()), dtype=torch.long) - first_ring[eid_ring]).to(a.dtype)
+    a_r, b_r, c_r = a[eid_ring], b[eid_ring], c[eid_ring]
+    T_r = rings[eid_ring]
+    # slab centre along a and the scaled semi-axes of its ellipse (quadricell.py:100-105)
+    delta_ring = (2 * a_r) / T_r
+    x = 0.5 * delta_ring + delta_ring * ring_pos
+    shrink = 1 - torch.square(x - a_r) / torch.square(a_r)
+    bs = torch.sqrt(shrink * torch.square(b_r))
+    cs = torch.sqrt(shrink * torch.square(c_r))
+    n_cells = torch.floor(_perimeter(bs, cs) / side[eid_ring])  # (quadricell.py:145-148)
+    dtheta = TWO_PI / n_cells
+    n_long = n_cells.to(torch.long)
+
+    pts = []
+    k = torch.arange(0, resolution - 1, dtype=a.dtype)
+    for s in range(0, eid_ring.shape[0], ring_chunk):
+        sl = slice(s, s + ring_chunk)
+        dth = dtheta[sl]
+        th = k[None, :] * dth[:, None]
+        ds = torch.sqrt(bs[sl, None] * torch.square(torch.sin(th)) + cs[sl, None] * torch.square(torch.cos(th)))
+        integ = torch.cumsum(torch.cat((torch.zeros(dth.shape[0], 1, dtype=a.dtype), ds * dth[:, None]), -1), -1)
+        table = TWO_PI * (integ / integ[:, -1:])  # [R, resolution]
+        n = n_long[sl]
+        nmax = int(n.max()) if n.numel() else 0
+        if nmax == 0:
+            continue
+        j = torch.arange(nmax, dtype=torch.long)
+        theta_cell = j[None, :] * dth[:, None]  # long * float -> float (quadricell.py:249)
+        live = j[None, :] < n[:, None]
+        theta_q = torch.where(live, theta_cell, torch.zeros_like(theta_cell))
+        cnt = torch.searchsorted(table[:, 1:].contiguous(), theta_q.contiguous(), right=False)
+        pick = torch.clamp(cnt - 1, min=0)
+        theta_p = torch.gather(table, 1, pick)
+        px = bs[sl, None] * torch.cos(theta_p)
+        py = cs[sl, None] * torch.sin(theta_p)
+        dr = delta_ring[sl, None]
+        pz = (0.5 * dr + dr * ring_pos[sl, None] - a_r[sl, None]).expand_as(px)
+        pts.append(torch.stack((px[live], py[live], pz[live]), -1))
+    points = torch.cat(pts, 0) if pts else torch.zeros(0, 3, dtype=a.dtype)
+    ellipsoid_id = torch.repeat_interleave(eid_ring, n_long)
+    return points, ellipsoid_id
+
+
+# ----------------------------------------------------------------------------------------------
+# a5  closed-form symmetric 3x3 eigen-decomposition -- sym_eig_3x3.py:246-307 (+ helpers :38-243)
+# ----------------------------------------------------------------------------------------------
+
+
+def _sgn(t):
+    return 2.0 * (t > 0.0).to(t.dtype) - 1.0
+
+
+def _null_vector(m, eps):
+    """eigenvector of the (near-)singular m = A - lambda I: largest of the three row cross
+    products, regularised by +-eps (sym_eig_3x3.py:112-143)."""
+    r0, r1, r2 = m[..., 0, :], m[..., 1, :], m[..., 2, :]
+    cr = torch.stack((torch.cross(r0, r1, dim=-1), torch.cross(r1, r2, dim=-1), torch.cross(r0, r2, dim=-1)), -2)
+    cr = cr + eps * _sgn(cr[..., :1, :])
+    n2 = (cr * cr).sum(-1)
+    best = n2.argmax(-1)
+    v = torch.gather(cr, -2, best[..., None, None].expand(*best.shape, 1, 3)).squeeze(-2)
+    nb = torch.gather(n2, -1, best[..., None])
+    return v / torch.sqrt(nb)
+
+
+def _perp_pair(w):
+    """unit u, v with {u, v, w} right handed (sym_eig_3x3.py:168-188): rotate w by pi/2 about
+    the axis of its smallest component, normalise, v = w x u."""
+    idx = w.abs().argmin(-1)
+    rots = torch.zeros(3, 3, 3, dtype=w.dtype)
+    for ax in range(3):
+        p, q = [i for i in range(3) if i != ax]
+        rots[ax, p, q] = -1.0
+        rots[ax, q, p] = 1.0
+    u = torch.nn.functional.normalize((rots[idx] @ w[..., None])[..., 0], dim=-1)
+    return u, torch.cross(w, u, dim=-1)
+
+
+def _second_vector(m, u, v, eps):
+    """eigenvector for the second eigenvalue inside span{u, v} (sym_eig_3x3.py:191-231)."""
+    J = torch.stack((u, v), -1)
+    red = J.transpose(-1, -2) @ m @ J
+    s = _sgn((red[..., 0, :] * red[..., 1, :]).sum(-1))
+    row = red[..., 0, :] + s[..., None] * red[..., 1, :]
+    row = row + eps * _sgn(row[..., :1])
+    quarter = torch.tensor([[0.0, -1.0], [1.0, 0.0]], dtype=row.dtype)
+    return (J @ torch.nn.functional.normalize(row @ quarter, dim=-1)[..., None])[..., 0]
+
+
+def _eigvec_triplet(A, l0, l1, eps):
+    eye = torch.eye(3, dtype=A.dtype)
+    e0 = _null_vector(A - l0[..., None, None] * eye, eps)
+    u, v = _perp_pair(e0)
+    e1 = _second_vector(A - l1[..., None, None] * eye, u, v, eps)
+    return e0, e1, torch.cross(e0, e1, dim=-1)
+
+
+def sym_eig_3x3(A: torch.Tensor, eigenvectors: bool = True, eps: Optional[float] = None):
+    """Eigenvalues ascending [...,3]; eigenvectors as columns [...,3,3] (sym_eig_3x3.py:246-307)."""
+    eps = eps or torch.finfo(torch.float).eps
+    if A.shape[-2:] != (3, 3):
+        raise ValueError("Only inputs of shape (..., 3, 3) are supported.")
+    diag = A.diagonal(dim1=-2, dim2=-1)
+    q = diag.sum(-1) / 3.0
+    p1 = ((A ** 2).sum((-1, -2)) - (diag ** 2).sum(-1)) / 2
+    p2 = ((diag - q[..., None]) ** 2).sum(-1) + 2.0 * p1.clamp(eps)
+    p = torch.sqrt(p2 / 6.0)
+    B = (A - q[..., None, None] * torch.eye(3, dtype=A.dtype)) / p[..., None, None]
+    r = (torch.det(B) / 2.0).clamp(-1.0 + eps, 1.0 - eps)
+    phi = torch.acos(r) / 3.0
+    big = q + 2 * p * torch.cos(phi)
+    small = q + 2 * p * torch.cos(phi + 2 * math.pi / 3)
+    mid = 3 * q - big - small
+    vals = torch.stack((small, mid, big), -1)
+    soft = torch.exp(-((p1 / (6 * eps)) ** 2))[..., None]
+    dsort, _ = torch.sort(diag, -1)
+    vals = soft * dsort + (1.0 - soft) * vals
+    if not eigenvectors:
+        return vals, None
+    t01 = torch.stack(_eigvec_triplet(A, vals[..., 0], vals[..., 1], eps), -1)
+    t21 = torch.stack(_eigvec_triplet(A, vals[..., 2], vals[..., 1], eps)[::-1], -1)
+    use01 = (vals[..., 1] - vals[..., 0]) > (vals[..., 2] - vals[..., 1])
+    return vals, torch.where(use01[..., None, None], t01, t21)
+
+
+# ----------------------------------------------------------------------------------------------
+# a4  kNN normals -- sampling.py:37-113
+# ----------------------------------------------------------------------------------------------
+
+
+def knn_normals(chunk: torch.Tensor, cloud: torch.Tensor, k: int = 20) -> torch.Tensor:
+    """Smallest-eigenvalue eigenvector of the centred kNN scatter matrix, majority-sign
+    disambiguated and normalised (sampling.py:62-113; :37-59)."""
+    d = torch.cdist(chunk[None], cloud[None], p=2.0)
+    _, nn = torch.topk(d, k, dim=2, largest=False)
+    nb = cloud[nn[0]]  # [m, k, 3]
+    ctr = nb - nb.mean(-2, keepdim=True)
+    scatter = ctr.mT @ ctr
+    _, vec = sym_eig_3x3(scatter[None], eigenvectors=True)
+    n = vec[0, :, :, 0]
+    npos = ((n[:, None, :] * ctr).sum(-1) > 0).to(n.dtype).sum(-1, keepdim=True)
+    n = (1.0 - 2.0 * (npos < 0.5 * k).to(n.dtype)) * n
+    # the reference normalises a stride-3 view of the stacked (n, y, z) frame (sampling.py:108-113);
+    # torch's strided norm reduction rounds differently from the contiguous one by <= 1 ulp, and a
+    # 1-ulp normal can flip a hemisphere test downstream -- keep the same memory layout.
+    nv = torch.stack((n, n, n), dim=2)[:, :, 0]
+    return nv / torch.linalg.norm(nv, dim=-1, keepdim=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# a7  rotate / hemisphere mask / ray build -- quadricell.py:322-386 (direction_mode "isocell")
+# ----------------------------------------------------------------------------------------------
+
+
+def rays_from_cells(points, eid, normals, centers, R):
+    """p' = R p; keep iff n_x * p'_x > 0; dir = normalise(R p); ori = p' + mu.
+
+    QUIRK reproduced on purpose: mask_quadricell (quadricell.py:337-340) forms the OUTER product
+    n[:, :, None] @ p'[:, None, :] and reads element [0, 0], so the "hemisphere" test only looks at
+    the x components (n_x * p'_x), not the full dot product n . p'."""
+    rp = (R[eid] @ points[..., None])[..., 0]
+    keep = (normals[eid][..., :, None] @ rp[..., None, :])[..., 0, 0] > 0
+    rp_k, eid_k = rp[keep], eid[keep]
+    d = torch.nn.functional.normalize((R[eid_k] @ points[keep][..., None])[..., 0], dim=-1)
+    return rp_k + centers[eid_k], d, eid_k
+
+
+# ----------------------------------------------------------------------------------------------
+# a8  SH colour -- sampling.py:116-124, utils/sh_utils.py:55-118
+# ----------------------------------------------------------------------------------------------
+
+_C0 = 0.28209479177387814
+_C1 = 0.4886025119029199
+_C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+_C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154,
+       -0.4570457994644658, 1.445305721320277, -0.5900435899266435)
+
+
+def sh_color(deg: int, sh: torch.Tensor, viewdir: torch.Tensor) -> torch.Tensor:
+    """rgb = max(SH(sh, -viewdir) + 0.5, 0); sh is [n, 3, 16] (channel, coefficient)."""
+    assert 0 <= deg <= 3, "oracle restates degrees 0-3 (active_sh_degree of 3DGS checkpoints)"
+    dirs = -viewdir
+    res = _C0 * sh[..., 0]
+    if deg > 0:
+        x, y, z = dirs[..., 0:1], dirs[..., 1:2], dirs[..., 2:3]
+        res = res - _C1 * y * sh[..., 1] + _C1 * z * sh[..., 2] - _C1 * x * sh[..., 3]
+    if deg > 1:
+        xx, yy, zz = x * x, y * y, z * z
+        xy, yz, xz = x * y, y * z, x * z
+        res = (res + _C2[0] * xy * sh[..., 4] + _C2[1] * yz * sh[..., 5]
+               + _C2[2] * (2.0 * zz - xx - yy) * sh[..., 6] + _C2[3] * xz * sh[..., 7]
+               + _C2[4] * (xx - yy) * sh[..., 8])
+    if deg > 2:
+        res = (res + _C3[0] * y * (3 * xx - yy) * sh[..., 9] + _C3[1] * xy * z * sh[..., 10]
+               + _C3[2] * y * (4 * zz - xx - yy) * sh[..., 11]
+               + _C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * sh[..., 12]
+               + _C3[4] * x * (4 * zz - xx - yy) * sh[..., 13] + _C3[5] * z * (xx - yy) * sh[..., 14]
+               + _C3[6] * x * (xx - 3 * yy) * sh[..., 15])
+    return torch.clamp_min(res + 0.5, 0.0)
+
+
+# ----------------------------------------------------------------------------------------------
+# a3 + driver  generate_all_possible_rays -- sampling.py:127-267
+# ----------------------------------------------------------------------------------------------
+
+
+def generate_rays(xyz, scaling_raw, rotation_raw, features, sh_degree: int = 3,
+                  target_points: int = 50, max_ellipsoids: Optional[int] = 1000,
+                  ellipsoid_idx: Optional[torch.Tensor] = None, k_neighbors: int = 20,
+                  generator: Optional[torch.Generator] = None, return_aux: bool = False):
+    """Scene -> candidate rays.  ``features`` is get_features, [N,16,3].
+    ``ellipsoid_idx`` indexes the VALID subset (as the reference's randperm does, :146-149)."""
+    scale = torch.exp(scaling_raw)
+    valid = mask_degraded_ellipsoids(scale[:, 0], scale[:, 1], scale[:, 2], target_points)
+    nvalid = int(torch.count_nonzero(valid))
+    if ellipsoid_idx is None:
+        cap = nvalid if max_ellipsoids is None else min(max_ellipsoids, nvalid)
+        ellipsoid_idx = torch.randperm(nvalid, dtype=torch.long, generator=generator)[:cap]
+    centers = xyz[valid][ellipsoid_idx]
+    normals = torch.cat([knn_normals(centers[s:s + 2500], centers, k_neighbors)
+                         for s in range(0, centers.shape[0], 2500)], 0)
+    sc = scale[valid][ellipsoid_idx]
+    points, eid = quadricell_centers(sc[:, 0], sc[:, 1], sc[:, 2], target_points)
+    R = quat_to_rotmat(rotation_raw)[valid][ellipsoid_idx]
+    ori, dirs, eid_k = rays_from_cells(points, eid, normals, centers, R)
+    gid = torch.arange(xyz.shape[0], dtype=torch.long)[valid][ellipsoid_idx][eid_k]
+    sh = features.transpose(1, 2).reshape(-1, 3, features.shape[1])[gid]
+    rgb = sh_color(sh_degree, sh, dirs).view(*dirs.shape)
+    if return_aux:
+        return ori, dirs, rgb, {"normals": normals, "points": points, "eid": eid, "eid_kept": eid_k,
+                                "gid": gid, "valid": valid, "ellipsoid_idx": ellipsoid_idx}
+    return ori, dirs, rgb
+
+
+# ----------------------------------------------------------------------------------------------
+# a10  ray feature MLP -- ray_preprocessor.py:3-46
+# ----------------------------------------------------------------------------------------------
+
+
+def positional_encoding(p: torch.Tensor, freqs: int) -> torch.Tensor:
+    """[sin(p_c * 2^f)] then [cos(...)], coordinate-major, no pi (ray_preprocessor.py:3-9)."""
+    bands = (2 ** torch.arange(freqs).float())
+    ang = (p[..., None] * bands).reshape(p.shape[:-1] + (freqs * p.shape[-1],))
+    return torch.cat([torch.sin(ang), torch.cos(ang)], -1)
+
+
+def ray_mlp_input(ori, dirs, rgb):
+    """141 = 9 raw + PE(ori,8) 48 + PE(dir,8) 48 + PE(rgb,6) 36 (ray_preprocessor.py:36-44)."""
+    return torch.cat([ori, dirs, rgb, positional_encoding(ori, 8), positional_encoding(dirs, 8),
+                      positional_encoding(rgb, 6)], -1)
+
+
+def ray_features(ori, dirs, rgb, w: dict) -> torch.Tensor:
+    """h = relu(W2 relu(W1 x)); out = W4 relu(W3 [h, x]) (ray_preprocessor.py:44-46).
+    ``w`` holds the IdentificationModule state_dict (keys ray_preprocessor.mlp.{0,2}.*, mlp2.{0,2}.*)."""
+    lin = torch.nn.functional.linear
+    x = ray_mlp_input(ori, dirs, rgb)
+    h = torch.relu(lin(x, w["ray_preprocessor.mlp.0.weight"], w["ray_preprocessor.mlp.0.bias"]))
+    h = torch.relu(lin(h, w["ray_preprocessor.mlp.2.weight"], w["ray_preprocessor.mlp.2.bias"]))
+    g = torch.relu(lin(torch.cat((h, x), -1), w["ray_preprocessor.mlp2.0.weight"], w["ray_preprocessor.mlp2.0.bias"]))
+    return lin(g, w["ray_preprocessor.mlp2.2.weight"], w["ray_preprocessor.mlp2.2.bias"])
+
+
+# ----------------------------------------------------------------------------------------------
+# a11  attention weights + score -- our_multihead_attention.py:4-12,70-79; identification_module.py:80-82
+# ----------------------------------------------------------------------------------------------
+
+
+def attention_scores(img_fea, ray_fea, w: dict, return_map: bool = True):
+    lin = torch.nn.functional.linear
+    q = lin(img_fea, w["attention.q_proj.weight"], w["attention.q_proj.bias"])
+    k = lin(ray_fea, w["attention.k_proj.weight"], w["attention.k_proj.bias"])
+    logits = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(q.shape[-1])
+    A = torch.nn.functional.softmax(logits, dim=-1)
+    score = A.sum(0)
+    return (score, A) if return_map else (score, None)
+
+
+def attention_scores_chunked(img_fea, ray_fea_fn, n_rays: int, w: dict, chunk: int = 29000):
+    """Same scores for ray sets too large for a materialised map: two sweeps over ray chunks with
+    per-token (max, sum-exp) merged across chunks.  ``ray_fea_fn(lo, hi)`` returns ray features.
+    Used by the uncapped CPU baseline."""
+    lin = torch.nn.functional.linear
+    q = lin(img_fea, w["attention.q_proj.weight"], w["attention.q_proj.bias"])
+    inv = 1.0 / math.sqrt(q.shape[-1])
+    m = torch.full((q.shape[0],), -float("inf"))
+    z = torch.zeros(q.shape[0])
+    ks = []
+    for lo in range(0, n_rays, chunk):
+        k = lin(ray_fea_fn(lo, min(lo + chunk, n_rays)), w["attention.k_proj.weight"], w["attention.k_proj.bias"])
+        ks.append(k)
+        L = (q @ k.t()) * inv
+        mc = torch.maximum(m, L.max(-1).values)
+        z = z * torch.exp(m - mc) + torch.exp(L - mc[:, None]).sum(-1)
+        m = mc
+    out = []
+    for k in ks:
+        L = (q @ k.t()) * inv
+        out.append((torch.exp(L - m[:, None]) / z[:, None]).sum(0))
+    return torch.cat(out), m, z
+
+
+# ----------------------------------------------------------------------------------------------
+# a13 / a14  LS line intersection and the pose tail -- line_intersection.py:5-34,75-154; test.py:157-198
+# ----------------------------------------------------------------------------------------------
+
+
+def line_intersection(points, directions, weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Least-squares intersection: R = sum w (I - d d^T), q = sum w (I - d d^T) o; NaN vector if
+    det(R) < 1e-7 (line_intersection.py:75-154)."""
+    P = torch.eye(3, dtype=points.dtype) - directions[:, :, None] * directions[:, None, :]
+    Pq = P @ points[:, :, None]
+    if weights is not None:
+        R = (P * weights[:, None, None]).sum(0)
+        q = (Pq * weights[:, None, None]).sum(0)
+    else:
+        R, q = P.sum(0), Pq.sum(0)
+    if torch.linalg.det(R) < 1.0e-7:
+        return torch.full((3,), float("nan"), dtype=R.dtype)
+    return torch.linalg.solve(R, q)[:, 0]
+
+
+def exclude_negatives(center, pts, dirs):
+    """keep rays whose direction points towards the centre (line_intersection.py:29-34)."""
+    return ((center[None] - pts) * dirs).sum(-1) > 0
+
+
+def make_rotation_mat(direction, up):
+    """rows [x; y; direction], x = norm(up x dir), y = norm(dir x x) (line_intersection.py:5-26)."""
+    xa = torch.linalg.cross(up, direction)
+    xa = xa / torch.linalg.norm(xa)
+    ya = torch.linalg.cross(direction, xa)
+    ya = ya / torch.linalg.norm(ya)
+    return torch.stack((xa, ya, direction), 0)
+
+
+def pose_tail(idx, weights, rays_ori, rays_dir, camera_up) -> Tuple[torch.Tensor, dict]:
+    """top-k rays -> c2w[4,4] (test.py:157-198): drop rays whose origin is repeated, unweighted LS,
+    exclude negatives, LS again (still unweighted), watch = norm(sum w d), rotation from
+    (-watch, up); singular rotation -> identity."""
+    o = rays_ori[idx]
+    uniq, counts = torch.unique(o, return_counts=True, dim=0)
+    keep = torch.isin(o, uniq[counts == 1], assume_unique=True).any(dim=1)
+    idx, weights = idx[keep], weights[keep]
+    o, d = rays_ori[idx], rays_dir[idx]
+    weights = weights / weights.sum()
+    c0 = line_intersection(o, d)
+    weights = weights * exclude_negatives(c0, o, d)
+    weights = weights / weights.sum()
+    c = line_intersection(o, d)
+    watch = (d * weights[:, None]).sum(0)
+    watch = watch / torch.linalg.norm(watch)
+    Rw2c = make_rotation_mat(-watch, camera_up)
+    if torch.linalg.det(Rw2c) < 1.0e-7:
+        Rw2c = torch.eye(3)
+    c2w = torch.eye(4, dtype=rays_ori.dtype)
+    c2w[:3, :3] = torch.linalg.inv(Rw2c)
+    c2w[:3, 3] = c
+    if torch.isnan(c2w).any():
+        c2w = torch.eye(4, dtype=rays_ori.dtype)
+    return c2w, {"idx": idx, "weights": weights, "center": c, "watch": watch}
