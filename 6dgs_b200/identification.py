@@ -1,0 +1,223 @@
+"""``IdentificationModule`` with the reference API (pose_estimation/identification_module.py:10-133)
+on top of the sm_100a kernels.
+
+Same sub-module and parameter names as the reference, so ``id_module.th`` state dicts load
+unchanged (``ray_preprocessor.mlp.{0,2}``, ``ray_preprocessor.mlp2.{0,2}``, ``attention.{q,k}_proj``,
+``camera_direction_prediction_network.*``, ``backbone_wrapper.*``).
+
+What changes underneath: the ray-feature MLP and the key projection do not depend on the
+query image (identification_module.py:79-80) but the reference recomputes them for every query.
+Here they are computed once per (rays, weights) pair into a key cache K[n_rays, 384] (fp32 or bf16);
+a query is then two streaming passes over K (per-token softmax statistics, then scores), a radix
+top-k and one fused pose-tail launch.  The [n_img, n_rays] attention map is only materialised when it
+is small (``attention_map_bytes_limit``); a 1M-Gaussian scene would need 30 GB.
+
+Training (autograd through the kernels) is out of scope for this path: calling
+``forward`` with gradients enabled on trainable parameters raises.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import BF16, F32
+from .camera_up import CameraDirectionPredictor
+from .image_tokens import BackboneWrapper
+
+
+class RayPreprocessor(torch.nn.Module):
+    """Parameter container + kernel call for the ray MLP (reference ray_preprocessor.py:11-46)."""
+
+    def __init__(self, viewpe: int = 8, pospe: int = 8, rgbpe: int = 6, featureC: int = 512, fea_output: int = 384):
+        super().__init__()
+        if (viewpe, pospe, rgbpe, featureC, fea_output) != (8, 8, 6, 512, 384):
+            raise NotImplementedError("the kernels are specialised for the reference configuration "
+                                      "(PE 8/8/6, width 512, output 384; identification_module.py:16-18)")
+        self.in_mlpC = 2 * viewpe * 3 + 3 + 2 * pospe * 3 + 3 + 2 * rgbpe * 3 + 3
+        relu = lambda: torch.nn.ReLU(inplace=True)  # noqa: E731
+        self.mlp = torch.nn.Sequential(torch.nn.Linear(self.in_mlpC, featureC), relu(),
+                                       torch.nn.Linear(featureC, featureC), relu())
+        self.mlp2 = torch.nn.Sequential(torch.nn.Linear(featureC + self.in_mlpC, featureC), relu(),
+                                        torch.nn.Linear(featureC, fea_output))
+        self.viewpe, self.pospe, self.rgbpe = viewpe, pospe, rgbpe
+
+    def _packed(self):
+        sd = {"ray_preprocessor." + k: v for k, v in self.state_dict().items()}
+        dev = self.mlp[0].weight.device
+        # identity q/k projections are never used by this module on its own
+        sd["attention.q_proj.weight"] = torch.zeros(384, 398, device=dev)
+        sd["attention.q_proj.bias"] = torch.zeros(384, device=dev)
+        sd["attention.k_proj.weight"] = torch.zeros(384, 384, device=dev)
+        sd["attention.k_proj.bias"] = torch.zeros(384, device=dev)
+        return ops.pack_ray_mlp_weights(sd, dev)
+
+    @torch.no_grad()
+    def forward(self, pts, viewdirs, rgb):
+        _, feat = ops.ray_features(pts, viewdirs, rgb, self._packed(), k_dtype=None, want_features=True, project=False)
+        return feat
+
+
+class MultiHeadAttention(torch.nn.Module):
+    """1-head attention WEIGHTS only (no V): softmax over rays of (Wq img)(Wk ray)^T / sqrt(384)
+    (reference our_multihead_attention.py:45-79)."""
+
+    def __init__(self, ray_fea_size: int, img_fea_size: int, embed_dim: int, num_heads: int = 1):
+        super().__init__()
+        assert embed_dim % num_heads == 0, "Embedding dimension must be 0 modulo number of heads."
+        if (ray_fea_size, img_fea_size, embed_dim, num_heads) != (384, 398, 384, 1):
+            raise NotImplementedError("kernels are specialised for 384-d single-head attention")
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
+        self.q_proj = torch.nn.Linear(img_fea_size, embed_dim)
+        self.k_proj = torch.nn.Linear(ray_fea_size, embed_dim)
+        torch.nn.init.xavier_uniform_(self.q_proj.weight)
+        self.q_proj.bias.data.fill_(0)
+        torch.nn.init.xavier_uniform_(self.k_proj.weight)
+        self.k_proj.bias.data.fill_(0)
+
+    @torch.no_grad()
+    def forward(self, img_features, ray_features, mask=None):
+        if mask is not None:
+            raise NotImplementedError("attention masks are never passed on the pose path (identification_module.py:80)")
+        dev = img_features.device
+        x = torch.zeros(img_features.shape[0], 400, device=dev)
+        x[:, :398] = img_features
+        wq = torch.zeros(384, 400, device=dev)
+        wq[:, :398] = self.q_proj.weight
+        q = ops.linear(x, wq, self.q_proj.bias.detach().contiguous())
+        k = ops.linear(ray_features.contiguous(), self.k_proj.weight.detach().contiguous(),
+                       self.k_proj.bias.detach().contiguous())
+        pm, pz = ops.score_pass1(k, q, ops.SCORE_SIMT)
+        m, z = ops.score_merge(pm, pz, q.shape[0])
+        _, amap = ops.score_pass2(k, q, m, z, ops.SCORE_SIMT, want_map=True)
+        return amap
+
+
+@dataclass
+class RayKeyCache:
+    """K[n_rays, 384] for one (ray set, weight version); the per-scene state of a query."""
+    keys: torch.Tensor
+    n_rays: int
+    tag: tuple
+    scores: Optional[torch.Tensor] = None  # reusable output buffer
+
+
+class IdentificationModule(torch.nn.Module):
+    def __init__(self, backbone_type: str = "dino", camera_up_output_augmentation=None,
+                 target_rays_dirs: Optional[torch.Tensor] = None, augmentation_channels: int = 10, *,
+                 backbone: Optional[torch.nn.Module] = None, score_impl: Optional[str] = None,
+                 attention_map_bytes_limit: int = 1 << 31):
+        super().__init__()
+        aug = getattr(camera_up_output_augmentation, "name", camera_up_output_augmentation)
+        if aug not in (None, "NONE"):
+            raise NotImplementedError("camera-up output augmentations are unused by the entry points "
+                                      "(pretrain_eval_attention.py:55-59 passes the default)")
+        self.backbone_wrapper = BackboneWrapper(backbone_type=backbone_type, backbone=backbone)
+        self.ray_preprocessor = RayPreprocessor(featureC=512, fea_output=self.backbone_wrapper.img_num_features)
+        self.camera_up_out_augmentation = None
+        self.camera_direction_prediction_network = CameraDirectionPredictor(
+            self.backbone_wrapper.img_num_features, self.backbone_wrapper.backbone_wh, fea_output=3)
+        self.attention = MultiHeadAttention(self.backbone_wrapper.img_num_features,
+                                            self.backbone_wrapper.img_num_features + 14,
+                                            self.backbone_wrapper.img_num_features, 1)
+        self.score_impl = score_impl or os.environ.get("SIXDGS_SCORE_IMPL", "simt_fp32")
+        if self.score_impl not in ("simt_fp32", "simt_bf16", "tc_bf16"):
+            raise ValueError("score_impl must be simt_fp32 | simt_bf16 | tc_bf16")
+        self.attention_map_bytes_limit = attention_map_bytes_limit
+        self._packed_cache = None
+        self._key_cache: Optional[RayKeyCache] = None
+
+    # ------------------------------------------------------------------ scene-side (per ray set)
+    def _hot_params(self):
+        return [self.ray_preprocessor.mlp[0], self.ray_preprocessor.mlp[2], self.ray_preprocessor.mlp2[0],
+                self.ray_preprocessor.mlp2[2], self.attention.q_proj, self.attention.k_proj]
+
+    def _weights_tag(self):
+        return tuple((p.data_ptr(), p._version) for lin in self._hot_params() for p in (lin.weight, lin.bias))
+
+    def packed_weights(self):
+        tag = self._weights_tag()
+        if self._packed_cache is None or self._packed_cache[0] != tag:
+            sd = {k: v for k, v in self.state_dict().items() if k.startswith(("ray_preprocessor.", "attention."))}
+            self._packed_cache = (tag, ops.pack_ray_mlp_weights(sd, self.attention.q_proj.weight.device))
+        return self._packed_cache[1]
+
+    @property
+    def _impl(self) -> int:
+        return ops.SCORE_TC if self.score_impl == "tc_bf16" else ops.SCORE_SIMT
+
+    @property
+    def _k_dtype(self) -> int:
+        return F32 if self.score_impl == "simt_fp32" else BF16
+
+    @torch.no_grad()
+    def build_key_cache(self, rays_ori, rays_dir, rays_rgb) -> RayKeyCache:
+        """rays -> PE -> MLP -> k_proj -> K (once per scene / weight update; the reference redoes this per query)."""
+        keys, _ = ops.ray_features(rays_ori, rays_dir, rays_rgb, self.packed_weights(), k_dtype=self._k_dtype)
+        return RayKeyCache(keys, keys.shape[0], ())
+
+    def _cache_for(self, rays_ori, rays_dir, rays_rgb) -> RayKeyCache:
+        tag = (rays_ori.data_ptr(), rays_dir.data_ptr(), rays_rgb.data_ptr(), rays_ori.shape[0], rays_ori._version,
+               rays_dir._version, rays_rgb._version, self.score_impl, self._weights_tag())
+        if self._key_cache is None or self._key_cache.tag != tag:
+            self._key_cache = self.build_key_cache(rays_ori, rays_dir, rays_rgb)
+            self._key_cache.tag = tag
+        return self._key_cache
+
+    # ------------------------------------------------------------------ query-side
+    @torch.no_grad()
+    def score_tokens(self, tokens_pe: torch.Tensor, cache: RayKeyCache, want_map: bool = False):
+        """[n_img,398] image tokens -> (scores[n_rays], attention_map or None, (m, z))."""
+        q = ops.project_queries(tokens_pe, self.packed_weights())
+        pm, pz = ops.score_pass1(cache.keys, q, self._impl)
+        m, z = ops.score_merge(pm, pz, q.shape[0])
+        scores, amap = ops.score_pass2(cache.keys, q, m, z, self._impl, want_map=want_map)
+        return scores, amap, (m, z)
+
+    def _camera_up(self, grid: torch.Tensor) -> torch.Tensor:
+        return torch.nn.functional.normalize(self.camera_direction_prediction_network(grid), dim=-1)
+
+    def run_attention(self, img, mask, rays_ori, rays_dir, rays_rgb):
+        """-> (score[n], attention_map[n_img,n] or None, features_img_flat[n_img,384], camera_up_dir[3])
+        (identification_module.py:77-92)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for lin in self._hot_params() for p in lin.parameters()):
+            raise NotImplementedError(
+                "autograd through the sm_100a kernels is out of scope for the pose-query path (SURVEY §8f-3); "
+                "call under torch.no_grad() / test_image(), or freeze the module (requires_grad_(False))")
+        with torch.no_grad():
+            tok_pe, tok, grid = self.backbone_wrapper(img, mask)
+            cache = self._cache_for(rays_ori, rays_dir, rays_rgb)
+            want_map = tok_pe.shape[0] * cache.n_rays * 4 <= self.attention_map_bytes_limit and self._impl == ops.SCORE_SIMT
+            score, amap, _ = self.score_tokens(tok_pe, cache, want_map)
+            up = self._camera_up(grid)
+        return score, amap, tok, up
+
+    def forward(self, img, mask, rays_ori, rays_dir, rays_rgb, rays_to_test: int = -1):
+        """Training-shaped variant (identification_module.py:94-115): random ray subset first."""
+        used = torch.randperm(rays_ori.shape[0], device=img.device, dtype=torch.long)
+        if rays_to_test != -1:
+            used = used[:rays_to_test]
+        scores, amap, tok, up = self.run_attention(img, mask, rays_ori[used], rays_dir[used], rays_rgb[used])
+        return scores, amap, tok, up, used
+
+    @torch.no_grad()
+    def test_image(self, img, mask, rays_ori, rays_dir, rays_rgb, rays_to_output: int = 100):
+        """-> (idx[k] int64, vals[k], scores[n], camera_up_dir[3], attention_map) (identification_module.py:117-133)."""
+        scores, amap, _, up = self.run_attention(img, mask, rays_ori, rays_dir, rays_rgb)
+        vals, idx = ops.topk(scores, rays_to_output)
+        return idx, vals, scores, up, amap
+
+    @torch.no_grad()
+    def query_pose(self, img, mask, rays_ori, rays_dir, rays_rgb, rays_to_output: int = 100,
+                   cache: Optional[RayKeyCache] = None):
+        """Fused query: image -> c2w[4,4] with no host synchronisation (test.py:85-198 in six launches
+        + backbone + up head).  Returns (c2w, aux) with aux = [centre3, watch3, n_kept, status]."""
+        cache = cache or self._cache_for(rays_ori, rays_dir, rays_rgb)
+        tok_pe, _, grid = self.backbone_wrapper(img, mask)
+        scores, _, _ = self.score_tokens(tok_pe, cache)
+        vals, idx = ops.topk(scores, rays_to_output)
+        up = self._camera_up(grid)
+        return ops.pose_tail(rays_ori, rays_dir, idx, vals, up)

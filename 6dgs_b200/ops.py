@@ -1,0 +1,195 @@
+"""Tensor-level wrappers over the C ABI (one function per kernel family).  torch is used for device
+memory and streams only; every computation below happens in libsixdgs.so."""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, FEAT, MAX_TOKENS, call, dptr, f32c, stream_ptr
+
+SCORE_SIMT = 0
+SCORE_TC = 1
+
+
+def degrade_mask(scaling_raw: torch.Tensor, target_points: int = 50) -> Tuple[torch.Tensor, torch.Tensor]:
+    s = f32c(scaling_raw)
+    n = s.shape[0]
+    valid = torch.empty(n, dtype=torch.uint8, device=s.device)
+    rings = torch.empty(n, dtype=torch.int32, device=s.device)
+    call("sixdgs_degrade_mask", dptr(s), n, target_points, dptr(valid, torch.uint8), dptr(rings, torch.int32), stream_ptr())
+    return valid.bool(), rings
+
+
+def knn_normals(cloud: torch.Tensor, k: int = 20, q_begin: int = 0, q_count: Optional[int] = None) -> torch.Tensor:
+    c = f32c(cloud)
+    m = c.shape[0]
+    q_count = m - q_begin if q_count is None else q_count
+    out = torch.empty(q_count, 3, dtype=torch.float32, device=c.device)
+    call("sixdgs_knn_normals", dptr(c), m, q_begin, q_count, k, dptr(out), stream_ptr())
+    return out
+
+
+def sym_eig3x3(A: torch.Tensor, eigenvectors: bool = True, eps: Optional[float] = None):
+    a = f32c(A).reshape(-1, 3, 3)
+    n = a.shape[0]
+    vals = torch.empty(n, 3, dtype=torch.float32, device=a.device)
+    vecs = torch.empty(n, 3, 3, dtype=torch.float32, device=a.device) if eigenvectors else None
+    call("sixdgs_sym_eig3x3", dptr(a), n, ctypes.c_float(eps or 0.0), dptr(vals), dptr(vecs), stream_ptr())
+    return vals, vecs
+
+
+def exclusive_scan(counts: torch.Tensor) -> torch.Tensor:
+    n = counts.shape[0]
+    out = torch.empty(n + 1, dtype=torch.int64, device=counts.device)
+    call("sixdgs_exclusive_scan", dptr(counts, torch.int32), n, dptr(out, torch.int64), stream_ptr())
+    return out
+
+
+def raygen(xyz, scaling_raw, rotation_raw, features, sh_degree: int, sel: torch.Tensor, normals: Optional[torch.Tensor],
+           target_points: int = 50, resolution: int = 1000, mode: int = 0):
+    """Two launches (count, fill) with one device->host read of the total ray count in between --
+    the same single sync the reference has at sampling.py:145."""
+    dev = scaling_raw.device
+    m = sel.shape[0]
+    rays_per = torch.empty(m, dtype=torch.int32, device=dev)
+    cells_per = torch.empty(m, dtype=torch.int32, device=dev)
+    s = stream_ptr()
+    call("sixdgs_raygen_count", dptr(xyz), dptr(scaling_raw), dptr(rotation_raw), dptr(sel, torch.int64), m,
+         dptr(normals), target_points, resolution, mode, dptr(rays_per, torch.int32), dptr(cells_per, torch.int32), s)
+    offs = exclusive_scan(rays_per)
+    n_rays = int(offs[-1].item())
+    ori = torch.empty(n_rays, 3, dtype=torch.float32, device=dev)
+    ell = torch.empty(n_rays, dtype=torch.int64, device=dev)
+    dirs = rgb = None
+    if mode == 0:
+        dirs = torch.empty(n_rays, 3, dtype=torch.float32, device=dev)
+        rgb = torch.empty(n_rays, 3, dtype=torch.float32, device=dev)
+    if n_rays:
+        call("sixdgs_raygen_fill", dptr(xyz), dptr(scaling_raw), dptr(rotation_raw), dptr(features), sh_degree,
+             dptr(sel, torch.int64), m, dptr(normals), target_points, resolution, mode, dptr(offs, torch.int64),
+             dptr(ori), dptr(dirs), dptr(rgb), dptr(ell, torch.int64), s)
+    return ori, dirs, rgb, ell, cells_per
+
+
+def pack_ray_mlp_weights(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
+    """Zero-pad the reference state-dict matrices so every reduction dim is a multiple of 16
+    (layout documented in include/sixdgs.h)."""
+    def g(k):
+        return sd[k].detach().to(device=device, dtype=torch.float32)
+
+    w1 = torch.zeros(512, 144, device=device)
+    w1[:, :141] = g("ray_preprocessor.mlp.0.weight")
+    w3 = torch.zeros(512, 656, device=device)
+    w3[:, :653] = g("ray_preprocessor.mlp2.0.weight")
+    wq = torch.zeros(FEAT, 400, device=device)
+    wq[:, :398] = g("attention.q_proj.weight")
+    return {
+        "w1p": w1.contiguous(), "b1": g("ray_preprocessor.mlp.0.bias").contiguous(),
+        "w2": g("ray_preprocessor.mlp.2.weight").contiguous(), "b2": g("ray_preprocessor.mlp.2.bias").contiguous(),
+        "w3p": w3.contiguous(), "b3": g("ray_preprocessor.mlp2.0.bias").contiguous(),
+        "w4": g("ray_preprocessor.mlp2.2.weight").contiguous(), "b4": g("ray_preprocessor.mlp2.2.bias").contiguous(),
+        "wk": g("attention.k_proj.weight").contiguous(), "bk": g("attention.k_proj.bias").contiguous(),
+        "wqp": wq.contiguous(), "bq": g("attention.q_proj.bias").contiguous(),
+    }
+
+
+def ray_features(ori, dirs, rgb, pw: Dict[str, torch.Tensor], k_dtype: Optional[int] = F32, want_features: bool = False,
+                 project: bool = True):
+    """-> (K cache [n,384] in k_dtype or None, features [n,384] fp32 or None)."""
+    ori, dirs, rgb = f32c(ori), f32c(dirs), f32c(rgb)
+    n = ori.shape[0]
+    dev = ori.device
+    k_out = None
+    if k_dtype is not None:
+        k_out = torch.empty(n, FEAT, dtype=torch.float32 if k_dtype == F32 else torch.bfloat16, device=dev)
+    feat = torch.empty(n, FEAT, dtype=torch.float32, device=dev) if want_features else None
+    wsz = int(_lib.load().sixdgs_ray_features_workspace(n))
+    ws = torch.empty(wsz, dtype=torch.uint8, device=dev)
+    call("sixdgs_ray_features", dptr(ori), dptr(dirs), dptr(rgb), n, dptr(pw["w1p"]), dptr(pw["b1"]), dptr(pw["w2"]),
+         dptr(pw["b2"]), dptr(pw["w3p"]), dptr(pw["b3"]), dptr(pw["w4"]), dptr(pw["b4"]),
+         dptr(pw["wk"]) if project else None, dptr(pw["bk"]) if project else None,
+         dptr(k_out, None), k_dtype if k_dtype is not None else F32, dptr(feat), dptr(ws, torch.uint8), wsz, stream_ptr())
+    return k_out, feat
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = False) -> torch.Tensor:
+    """y = act(x w^T + b); x [m,k] with k % 16 == 0 (pad on the caller side)."""
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty(m, n, dtype=torch.float32, device=x.device)
+    call("sixdgs_linear", dptr(x), m, k, k, dptr(w), dptr(b), n, dptr(y), n, int(relu), stream_ptr())
+    return y
+
+
+def project_queries(img_fea: torch.Tensor, pw: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """q = Wq [f_img | pe] + bq (our_multihead_attention.py:74); 398 -> 400 zero pad."""
+    n_img = img_fea.shape[0]
+    x = torch.zeros(n_img, 400, dtype=torch.float32, device=img_fea.device)
+    x[:, :398] = img_fea
+    return linear(x, pw["wqp"], pw["bq"])
+
+
+def _kdtype(k: torch.Tensor) -> int:
+    if k.dtype == torch.float32:
+        return F32
+    if k.dtype == torch.bfloat16:
+        return BF16
+    raise _lib.SixdgsError(f"key cache must be float32 or bfloat16, got {k.dtype}")
+
+
+def score_pass1(k_cache: torch.Tensor, q: torch.Tensor, impl: int = SCORE_SIMT):
+    parts = int(_lib.load().sixdgs_score_parts(impl))
+    pm = torch.empty(parts, MAX_TOKENS, dtype=torch.float32, device=q.device)
+    pz = torch.empty(parts, MAX_TOKENS, dtype=torch.float32, device=q.device)
+    call("sixdgs_score_pass1", dptr(k_cache, None), _kdtype(k_cache), k_cache.shape[0], dptr(q), q.shape[0], dptr(pm),
+         dptr(pz), impl, stream_ptr())
+    return pm, pz
+
+
+def score_merge(pm: torch.Tensor, pz: torch.Tensor, n_img: int):
+    m = torch.empty(MAX_TOKENS, dtype=torch.float32, device=pm.device)
+    z = torch.empty(MAX_TOKENS, dtype=torch.float32, device=pm.device)
+    call("sixdgs_score_merge", dptr(pm), dptr(pz), pm.shape[0], n_img, dptr(m), dptr(z), stream_ptr())
+    return m, z
+
+
+def score_pass2(k_cache: torch.Tensor, q: torch.Tensor, m: torch.Tensor, z: torch.Tensor, impl: int = SCORE_SIMT,
+                want_map: bool = False, out: Optional[torch.Tensor] = None):
+    n = k_cache.shape[0]
+    scores = out if out is not None else torch.empty(n, dtype=torch.float32, device=q.device)
+    amap = torch.empty(q.shape[0], n, dtype=torch.float32, device=q.device) if want_map else None
+    call("sixdgs_score_pass2", dptr(k_cache, None), _kdtype(k_cache), n, dptr(q), q.shape[0], dptr(m), dptr(z),
+         dptr(scores), dptr(amap), impl, stream_ptr())
+    return scores, amap
+
+
+def topk(scores: torch.Tensor, k: int):
+    n = scores.shape[0]
+    vals = torch.empty(k, dtype=torch.float32, device=scores.device)
+    idx = torch.empty(k, dtype=torch.int64, device=scores.device)
+    wsz = int(_lib.load().sixdgs_topk_workspace(n, k))
+    ws = torch.empty(wsz, dtype=torch.uint8, device=scores.device)
+    call("sixdgs_topk", dptr(scores), n, k, dptr(vals), dptr(idx, torch.int64), dptr(ws, torch.uint8), wsz, stream_ptr())
+    return vals, idx
+
+
+def line_intersect(points: torch.Tensor, dirs: torch.Tensor, weights: Optional[torch.Tensor] = None):
+    p, d = f32c(points), f32c(dirs)
+    w = f32c(weights) if weights is not None else None
+    centre = torch.empty(3, dtype=torch.float32, device=p.device)
+    status = torch.zeros(1, dtype=torch.int32, device=p.device)
+    ws = torch.empty(12, dtype=torch.float64, device=p.device)
+    call("sixdgs_line_intersect", dptr(p), dptr(d), dptr(w), p.shape[0], dptr(centre), dptr(status, torch.int32),
+         dptr(ws, torch.float64), stream_ptr())
+    return centre, status
+
+
+def pose_tail(rays_ori, rays_dir, idx, vals, up):
+    c2w = torch.empty(4, 4, dtype=torch.float32, device=rays_ori.device)
+    aux = torch.empty(8, dtype=torch.float32, device=rays_ori.device)
+    call("sixdgs_pose_tail", dptr(rays_ori), dptr(rays_dir), dptr(idx, torch.int64), dptr(vals), idx.shape[0],
+         dptr(f32c(up)), dptr(c2w), dptr(aux), stream_ptr())
+    return c2w, aux

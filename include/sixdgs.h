@@ -1,0 +1,148 @@
+/*
+ * sixdgs.h -- C ABI of libsixdgs.so: the B200 (sm_100a) kernels behind the 6DGS single-query
+ * pose-estimation hot path.
+ *
+ * The reference (mbortolon97/6dgs) has NO native boundary on this path -- it is pure torch ops in
+ * pose_estimation/*.py -- so the entry points below are what a ctypes/pybind binding inside the
+ * reference's Python functions would call.  The calling convention follows the
+ * reference's only native precedent, free functions over raw device pointers
+ * (submodules/simple-knn/simple_knn.h:18, spatial.cu:15-26).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory
+ *     (inputs, outputs, workspaces); the library never allocates or frees device memory and keeps
+ *     no global state except a thread-local last-error string;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no implicit device sync;
+ *   - return 0 on success, negative SIXDGS_E* otherwise; never throws across the ABI;
+ *   - numerical singularities are not errors: they follow the reference conventions (NaN centre
+ *     when det(R) < 1e-7, identity rotation when the frame is singular) and raise a status flag;
+ *   - row-major fp32 everywhere unless a dtype argument says otherwise; ray/ellipsoid indices int64
+ *     (the reference uses torch.long).
+ */
+#ifndef SIXDGS_H
+#define SIXDGS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIXDGS_OK 0
+#define SIXDGS_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported dtype)   */
+#define SIXDGS_ECUDA (-2)    /* a CUDA runtime call or launch failed; see sixdgs_last_error()   */
+#define SIXDGS_EWORKSPACE (-3) /* workspace too small                                            */
+#define SIXDGS_EUNSUPPORTED (-4) /* device is not sm_100 / feature not available                 */
+
+#define SIXDGS_F32 0
+#define SIXDGS_BF16 1
+
+#define SIXDGS_FEAT 384      /* ray / image embedding width (DINOv2 ViT-S/14), backbone.py:17  */
+#define SIXDGS_MAX_TOKENS 256 /* 16x16 backbone grid, backbone.py:16                            */
+
+int sixdgs_version(void);
+const char* sixdgs_last_error(void);
+/* 1 if the current device can run the tcgen05/TMA kernels (compute capability 10.x). */
+int sixdgs_device_supported(void);
+
+/* ---- a2: degrade mask + ring layout -------- reference pose_estimation/quadricell.py:171-188 ----
+ * scaling_raw[n,3] is the LOG scale (GaussianModel._scaling; get_scaling = exp, gaussian_model.py:125).
+ * valid[i] = rings(i) < target.  rings_out (nullable) receives the slab count. */
+int sixdgs_degrade_mask(const float* scaling_raw, int64_t n, int target_points,
+                        uint8_t* valid, int32_t* rings_out, void* stream);
+
+/* ---- a4: exact k-nearest-neighbour normals -------- pose_estimation/sampling.py:37-113 ----------
+ * cloud[m,3]; for query rows [q_begin, q_begin+q_count) writes normals_out[q_count,3]: the
+ * smallest-eigenvalue eigenvector (a5) of the centred k-NN scatter matrix, majority-sign
+ * disambiguated, normalised.  k <= 32.  Brute force, exact (the reference uses cdist + topk). */
+int sixdgs_knn_normals(const float* cloud, int64_t m, int64_t q_begin, int64_t q_count, int k,
+                       float* normals_out, void* stream);
+
+/* ---- a5: batched closed-form symmetric 3x3 eigen-decomposition --- pose_estimation/sym_eig_3x3.py:246-307
+ * A[n,3,3] -> vals[n,3] ascending, vecs[n,3,3] (eigenvectors as COLUMNS; nullable). */
+int sixdgs_sym_eig3x3(const float* A, int64_t n, float eps, float* vals, float* vecs, void* stream);
+
+/* ---- a6+a7+a8: candidate-ray generation -------- quadricell.py:191-386, sampling.py:116-124,176-251,
+ *                                                  utils/sh_utils.py:55-118, general_utils.py:103-126
+ * sel[m] = global Gaussian ids of the selected (valid, permuted) ellipsoids; normals[m,3] from a4.
+ * Count mode: rays_per_ell[m] and cells_per_ell[m] (nullable) are written.
+ * Fill mode:  ray_offset[m] = exclusive scan of rays_per_ell; writes ori/dir/rgb[n_rays,3] and
+ *             ell_id[n_rays] (local index into sel; nullable) in ellipsoid-, ring-, cell-major order.
+ * mode 0 = rays (rotate, hemisphere quirk n_x*p'_x > 0, normalise, +mu, SH colour);
+ * mode 1 = raw quadricell cells (a6 only: un-rotated points -> ori, no mask; dir/rgb untouched). */
+int sixdgs_raygen_count(const float* xyz, const float* scaling_raw, const float* rotation_raw,
+                        const int64_t* sel, int64_t m, const float* normals, int target_points,
+                        int resolution, int mode, int32_t* rays_per_ell, int32_t* cells_per_ell,
+                        void* stream);
+int sixdgs_raygen_fill(const float* xyz, const float* scaling_raw, const float* rotation_raw,
+                       const float* features /* [N,16,3] = get_features */, int sh_degree,
+                       const int64_t* sel, int64_t m, const float* normals, int target_points,
+                       int resolution, int mode, const int64_t* ray_offset, float* ori, float* dir,
+                       float* rgb, int64_t* ell_id, void* stream);
+/* exclusive scan int32 -> int64 with the total in out[n] (out has n+1 entries).  Single block. */
+int sixdgs_exclusive_scan(const int32_t* in, int64_t n, int64_t* out, void* stream);
+
+/* ---- a10 (+ k_proj of a11): ray features -> key cache -------- ray_preprocessor.py:3-46,
+ *                                                               our_multihead_attention.py:75
+ * Packed weights (built once by the host, zero padded so every K dim is a multiple of 16):
+ *   w1p[512,144]  = mlp.0.weight  (141 -> 144)        b1[512]
+ *   w2 [512,512]  = mlp.2.weight                      b2[512]
+ *   w3p[512,656]  = mlp2.0.weight ([h512 | x141] -> 656) b3[512]
+ *   w4 [384,512]  = mlp2.2.weight                     b4[384]
+ *   wk [384,384]  = attention.k_proj.weight (nullable: skip projection, emit features) bk[384]
+ * k_out[n,384] in k_dtype (SIXDGS_F32 | SIXDGS_BF16); feat_out (nullable) = pre-projection features.
+ * workspace >= sixdgs_ray_features_workspace(n) bytes. */
+size_t sixdgs_ray_features_workspace(int64_t n);
+int sixdgs_ray_features(const float* ori, const float* dir, const float* rgb, int64_t n,
+                        const float* w1p, const float* b1, const float* w2, const float* b2,
+                        const float* w3p, const float* b3, const float* w4, const float* b4,
+                        const float* wk, const float* bk, void* k_out, int k_dtype, float* feat_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* generic y[m,n] = act(x[m,k] w[n,k]^T + b[n]); k % 16 == 0, lda/ldc in elements (used for q_proj,
+ * our_multihead_attention.py:74, with img features padded 398 -> 400). */
+int sixdgs_linear(const float* x, int64_t m, int k, int lda, const float* w, const float* b, int n,
+                  float* y, int ldc, int relu, void* stream);
+
+/* ---- a11: softmax-over-rays attention score -------- our_multihead_attention.py:4-12,70-79;
+ *                                                      identification_module.py:80-82
+ * q[n_img,384] fp32 (already projected), K cache [n_rays,384] in k_dtype.
+ * pass1: per-token running (max, sum-exp) of logits q.k/sqrt(384) over this K shard, written as
+ *        `n_parts` partial rows part_m/part_z[n_parts, 256] (n_parts = sixdgs_score_parts()).
+ * merge: log-sum-exp merge of partial rows (also used across ranks after an all-gather) -> m,z[256].
+ * pass2: scores[r] = sum_i exp(L_ir - m_i) / z_i; attn_map (nullable) [n_img, n_rays].
+ * impl: 0 = SIMT fp32 (exact path), 1 = tcgen05 bf16 tensor cores (K must be bf16). */
+int sixdgs_score_parts(int impl);
+int sixdgs_score_pass1(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_img,
+                       float* part_m, float* part_z, int impl, void* stream);
+int sixdgs_score_merge(const float* part_m, const float* part_z, int n_parts, int n_img, float* m,
+                       float* z, void* stream);
+int sixdgs_score_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_img,
+                       const float* m, const float* z, float* scores, float* attn_map, int impl,
+                       void* stream);
+
+/* ---- a12: top-k -------- identification_module.py:131 (torch.topk, sorted descending) -----------
+ * workspace >= sixdgs_topk_workspace(n, k).  idx int64, ties broken by lower index first. */
+size_t sixdgs_topk_workspace(int64_t n, int k);
+int sixdgs_topk(const float* scores, int64_t n, int k, float* vals, int64_t* idx, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* ---- a13: least-squares line intersection -------- line_intersection.py:75-154 ------------------
+ * R = sum w (I - d d^T), q = sum w (I - d d^T) o, centre = solve(R, q); NaN x3 and *status |= 1 when
+ * det(R) < 1e-7.  weights nullable (the live call sites pass none, test.py:169-179).  Any n (the
+ * weighted all-ray form is the one least_squared_loss.py:62-64 specifies). */
+int sixdgs_line_intersect(const float* points, const float* dirs, const float* weights, int64_t n,
+                          float* centre, int32_t* status, void* workspace /* 12 doubles */, void* stream);
+
+/* ---- a14: pose tail -------- pose_estimation/test.py:157-198, line_intersection.py:5-34 --------
+ * top-k candidates (idx into rays_ori/rays_dir, vals = scores) + camera up -> c2w[16] row-major.
+ * aux (nullable, 8 floats): centre[3], watch[3], n_kept, status (bit0 NaN centre, bit1 singular
+ * rotation -> identity, bit2 NaN c2w -> identity).  k <= 1024. */
+int sixdgs_pose_tail(const float* rays_ori, const float* rays_dir, const int64_t* idx,
+                     const float* vals, int k, const float* up, float* c2w, float* aux, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIXDGS_H */
