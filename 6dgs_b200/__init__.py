@@ -19,6 +19,7 @@ from .pose_solve import (compute_line_intersection_impl2, exclude_negatives, mak
                          pose_from_topk)
 from .raygen import generate_all_possible_rays, quadricell_cells  # noqa: F401
 from .scene import GaussianScene  # noqa: F401
+from .sharding import CudaBackend, ShardedPoseEstimator  # noqa: F401
 
 test_pose_estimation.__test__ = False  # not a pytest test despite the reference's name
 

@@ -17,9 +17,11 @@ int score_simt_pass1(const void*, int, int64_t, const float*, int, float*, float
 int score_simt_pass2(const void*, int, int64_t, const float*, int, const float*, const float*, float*, float*,
                      cudaStream_t);
 int score_simt_parts();
-int score_tc_pass1(const void*, int64_t, const float*, int, float*, float*, cudaStream_t);
-int score_tc_pass2(const void*, int64_t, const float*, int, const float*, const float*, float*, cudaStream_t);
+int score_tc_pass1(const void*, int64_t, const float*, int, float*, float*, void*, size_t, cudaStream_t);
+int score_tc_pass2(const void*, int64_t, const float*, int, const float*, const float*, float*, void*, size_t,
+                   cudaStream_t);
 int score_tc_parts();
+size_t score_tc_workspace();
 
 }  // namespace sixdgs
 
@@ -36,6 +38,7 @@ extern "C" int sixdgs_device_supported(void) {
 }
 
 extern "C" int sixdgs_score_parts(int impl) { return impl == 1 ? score_tc_parts() : score_simt_parts(); }
+extern "C" size_t sixdgs_score_workspace(int impl) { return impl == 1 ? score_tc_workspace() : 0; }
 
 static int check_score_args(const void* k, int k_dtype, int64_t n_rays, const float* q, int n_img, int impl) {
   SIXDGS_REQUIRE(k && q, "null pointer");
@@ -48,23 +51,25 @@ static int check_score_args(const void* k, int k_dtype, int64_t n_rays, const fl
 }
 
 extern "C" int sixdgs_score_pass1(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_img,
-                                  float* part_m, float* part_z, int impl, void* stream) {
+                                  float* part_m, float* part_z, int impl, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   int rc = check_score_args(k_cache, k_dtype, n_rays, q, n_img, impl);
   if (rc) return rc;
   SIXDGS_REQUIRE(part_m && part_z, "null pointer");
-  if (impl == 1) return score_tc_pass1(k_cache, n_rays, q, n_img, part_m, part_z, (cudaStream_t)stream);
+  if (impl == 1)
+    return score_tc_pass1(k_cache, n_rays, q, n_img, part_m, part_z, workspace, workspace_bytes, (cudaStream_t)stream);
   return score_simt_pass1(k_cache, k_dtype, n_rays, q, n_img, part_m, part_z, (cudaStream_t)stream);
 }
 
 extern "C" int sixdgs_score_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_img,
                                   const float* m, const float* z, float* scores, float* attn_map, int impl,
-                                  void* stream) {
+                                  void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_score_args(k_cache, k_dtype, n_rays, q, n_img, impl);
   if (rc) return rc;
   SIXDGS_REQUIRE(m && z && scores, "null pointer");
   if (impl == 1) {
     SIXDGS_REQUIRE(attn_map == nullptr, "impl 1 does not materialise the attention map");
-    return score_tc_pass2(k_cache, n_rays, q, n_img, m, z, scores, (cudaStream_t)stream);
+    return score_tc_pass2(k_cache, n_rays, q, n_img, m, z, scores, workspace, workspace_bytes, (cudaStream_t)stream);
   }
   return score_simt_pass2(k_cache, k_dtype, n_rays, q, n_img, m, z, scores, attn_map, (cudaStream_t)stream);
 }

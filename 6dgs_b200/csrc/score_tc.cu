@@ -1,13 +1,433 @@
-// placeholder for the tcgen05 ray-score kernel (filled in by the next milestone)
+// a11, throughput path: softmax-over-rays attention scores on the 5th-gen tensor cores.
+// Reference: pose_estimation/our_multihead_attention.py:4-12,70-79; identification_module.py:80-82.
+//
+// Work shape.  One query = 256 image tokens x n_rays keys of width 384.  With the key cache in bf16
+// the arithmetic intensity is 2*256*384 FLOP per 768-byte key = 256 FLOP/B, i.e. right at the B200
+// ridge (~253 FLOP/B from the measured 1.66 PFLOP/s and 6.57 TB/s): the kernel has to keep HBM, the
+// tensor pipe and the MUFU (one exp2 per logit) busy at the same time.
+//
+// Design (persistent, one CTA per SM, CTA pairs = clusters of 2, tcgen05 cta_group::2):
+//   * Q (256 x 384 bf16 = 192 KB) does not fit next to a K pipeline in one SM, so each CTA of a pair
+//     keeps HALF of Q (128 tokens, 96 KB) resident in shared memory for the whole kernel and the pair
+//     issues M=256 x N=256 x K=16 UMMAs that read both halves;
+//   * every pair-tile is 256 rays: each CTA TMA-loads its own 128 rays as six 128x64 bf16 k-blocks
+//     (16 KB, SWIZZLE_128B) through a 7-stage mbarrier ring -> every key byte crosses HBM->SM once;
+//   * accumulators live in TMEM (128 lanes x 256 fp32 columns per CTA), double buffered (512 cols),
+//     so the epilogue of tile t overlaps the MMAs of tile t+1;
+//   * pass 1 issues D = Q K^T  (lanes = tokens, columns = rays): each epilogue thread owns one token
+//     and folds its columns into a running (max, sum-exp2) -- no cross-lane traffic;
+//     pass 2 issues D = K Q^T  (lanes = rays, columns = tokens): each thread owns one ray and sums
+//     exp2(s - c_token) over the tokens, c = max + log2(sum) broadcast from shared memory.
+//     The operands are the same shared-memory tiles in both passes (both are K-major), only the A/B
+//     roles swap, which is what lets both reductions stay thread-local.
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM allocator,
+//     4..11 = epilogue (two warps per TMEM lane quadrant, 128 columns each).
+// log2(e)/sqrt(384) is folded into Q when it is converted to bf16, so the epilogue is FADD + MUFU.EX2
+// + FADD per logit.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "common.cuh"
+
 namespace sixdgs {
-int score_tc_parts() { return kNumSMs; }
-int score_tc_pass1(const void*, int64_t, const float*, int, float*, float*, cudaStream_t) {
-  set_error("score_tc: not built yet");
-  return SIXDGS_EUNSUPPORTED;
+
+constexpr int kTcStages = 7;
+constexpr int kTcTileRays = 256;               // rays per CTA-pair tile
+constexpr int kTcKBlocks = kFeat / 64;          // 6 k-blocks of 64 bf16 (128 B rows)
+constexpr int kTcKBBytes = 128 * 128;           // 128 rows x 128 B
+constexpr int kTcThreads = 384;
+constexpr int kTcPairs = kNumSMs / 2;           // 74 clusters
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kQScale = 1.4426950408889634f / 19.595917942265423f;  // log2(e) / sqrt(384)
+
+struct __align__(1024) TcSmem {
+  uint8_t q[kTcKBlocks][kTcKBBytes];       //  96 KB: this CTA's 128 tokens
+  uint8_t k[kTcStages][kTcKBBytes];        // 112 KB: K pipeline
+  uint64_t full[kTcStages];
+  uint64_t empty[kTcStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t q_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+  float cst[kMaxTokens];                   // pass 2: c_token = m*log2e + log2 z  (+inf for padded tokens)
+  float xch[2][128];                       // column-half exchange
+  float xch2[2][128];
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
-int score_tc_pass2(const void*, int64_t, const float*, int, const float*, const float*, float*, cudaStream_t) {
-  set_error("score_tc: not built yet");
-  return SIXDGS_EUNSUPPORTED;
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "LAB_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra LAB_WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit: address of the pair leader's barrier
+
+// 2-CTA TMA load: both CTAs issue it for their own shared memory; the transaction bytes are
+// accounted on the LEADER's mbarrier.
+__device__ __forceinline__ void tma_load_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1, LBO 16 B (unused),
+// SBO = 1024 B between 8-row groups, layout type 2).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16, bf16 x bf16 -> fp32, A and B K-major, M = 256 (cta_group::2), N = 256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+// signal the barrier at this offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+        "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+        "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr));
+}
+// The destination registers of tcgen05.ld are written asynchronously; tying all 32 of them to the wait
+// as in/out operands stops the compiler from scheduling any use of them above the wait.
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                 "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
+                 "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------ Q preparation
+// Qb[t, :] = bf16(q[t, :] * log2(e)/sqrt(384)) for t < n_img, 0 otherwise  (256 x 384)
+__global__ void tc_qprep_kernel(const float* __restrict__ q, int n_img, __nv_bfloat16* __restrict__ qb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kMaxTokens * kFeat) return;
+  const int t = i / kFeat;
+  qb[i] = __float2bfloat16_rn(t < n_img ? q[i] * kQScale : 0.0f);
+}
+
+// ------------------------------------------------------------------------------------ main kernel
+template <int PASS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_q,
+                int64_t n_rays, int n_img,
+                float* __restrict__ part_m, float* __restrict__ part_z,     // pass 1 out [pairs, 256]
+                const float* __restrict__ gm, const float* __restrict__ gz, // pass 2 in  [256]
+                float* __restrict__ scores) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+  const int64_t n_tiles = (n_rays + kTcTileRays - 1) / kTcTileRays;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_k)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&sm.full[s], 2);   // leader's expect_tx arrive + peer's remote arrive
+      mbar_init(&sm.empty[s], 1);  // one multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&sm.tmem_full[a], 1);    // one multicast tcgen05.commit
+      mbar_init(&sm.tmem_empty[a], 16);  // 8 epilogue warps x 2 CTAs (lane 0 of each), leader's copy is used
+    }
+    mbar_init(&sm.q_full, 2);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (PASS == 2) {
+    for (int t = tid; t < kMaxTokens; t += kTcThreads)
+      sm.cst[t] = (t < n_img) ? (gm[t] * kLog2e + log2f(gz[t])) : INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      // resident half of Q: rows [128*rank, 128*rank+128), six k-blocks, accounted on the leader's q_full
+      if (leader) mbar_arrive_expect_tx(&sm.q_full, 2 * kTcKBlocks * kTcKBBytes);
+      else mbar_arrive_cluster(&sm.q_full, 0);
+      for (int kb = 0; kb < kTcKBlocks; ++kb) tma_load_2sm(sm.q[kb], &tmap_q, &sm.q_full, kb * 64, (int)rank * 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
+        const int row0 = (int)(tile * kTcTileRays + rank * 128);
+        for (int kb = 0; kb < kTcKBlocks; ++kb) {
+          mbar_wait(&sm.empty[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&sm.full[stage], 2 * kTcKBBytes);
+          else mbar_arrive_cluster(&sm.full[stage], 0);
+          tma_load_2sm(sm.k[stage], &tmap_k, &sm.full[stage], kb * 64, row0);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA, one thread) ================================
+    if (leader && lane == 0) {
+      mbar_wait(&sm.q_full, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+        const int acc = (int)(it & 1);
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < kTcKBlocks; ++kb) {
+          mbar_wait(&sm.full[stage], phase);
+          tc_fence_after();
+          const uint32_t qa = smem_u32(sm.q[kb]);
+          const uint32_t ka = smem_u32(sm.k[stage]);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t dq = umma_desc_sw128(qa + k4 * 32);
+            const uint64_t dk = umma_desc_sw128(ka + k4 * 32);
+            if (PASS == 1) umma_2sm(tmem_d, dq, dk, (uint32_t)((kb | k4) != 0));  // D[token, ray]
+            else umma_2sm(tmem_d, dk, dq, (uint32_t)((kb | k4) != 0));            // D[ray, token]
+          }
+          umma_commit_2sm(&sm.empty[stage]);  // frees this K stage in both CTAs when the MMAs retire
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&sm.tmem_full[acc]);  // accumulator ready for both CTAs' epilogues
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================ epilogue (both CTAs, 8 warps) ================================
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may touch
+    const int half = (warp - 4) >> 2;   // which 128 columns
+    const int row = quad * 32 + lane;   // TMEM lane == token (pass 1) / ray within the CTA's 128 (pass 2)
+    float run_m = -INFINITY, run_z = 0.f;
+    int64_t it = 0;
+    for (int64_t tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      mbar_wait(&sm.tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + half * 128);
+      float va[32], vb[32];
+      if (PASS == 1) {
+        const int64_t col0 = tile * kTcTileRays + half * 128;  // first ray of this warp's columns
+        const int valid = (int)min((int64_t)128, max((int64_t)0, n_rays - col0));
+        tmem_ld32(taddr, va);
+        tmem_ld_wait(va);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float(&cur)[32] = (c & 1) ? vb : va;
+          float(&nxt)[32] = (c & 1) ? va : vb;
+          if (c + 1 < 4) tmem_ld32(taddr + (c + 1) * 32, nxt);
+          const int nv = valid - c * 32;  // columns of this chunk that are real rays
+          if (nv > 0) {
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (j < nv) ? cur[j] : -INFINITY);
+            const float mn = fmaxf(run_m, cm);
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += (j < nv) ? ex2(cur[j] - mn) : 0.f;
+            run_z = run_z * ex2(run_m - mn) + s;
+            run_m = mn;
+          }
+          if (c + 1 < 4) tmem_ld_wait(nxt);
+        }
+      } else {
+        float s = 0.f;
+        tmem_ld32(taddr, va);
+        tmem_ld_wait(va);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float(&cur)[32] = (c & 1) ? vb : va;
+          float(&nxt)[32] = (c & 1) ? va : vb;
+          if (c + 1 < 4) tmem_ld32(taddr + (c + 1) * 32, nxt);
+          const float4* cc = reinterpret_cast<const float4*>(&sm.cst[half * 128 + c * 32]);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 c4 = cc[j4];
+            s += ex2(cur[j4 * 4 + 0] - c4.x);
+            s += ex2(cur[j4 * 4 + 1] - c4.y);
+            s += ex2(cur[j4 * 4 + 2] - c4.z);
+            s += ex2(cur[j4 * 4 + 3] - c4.w);
+          }
+          if (c + 1 < 4) tmem_ld_wait(nxt);
+        }
+        // combine the two column halves of each ray, then one coalesced 128-float store per CTA
+        if (half == 1) sm.xch[acc][row] = s;
+        epi_bar_sync();
+        if (half == 0) {
+          const int64_t ray = tile * kTcTileRays + rank * 128 + row;
+          if (ray < n_rays) scores[ray] = s + sm.xch[acc][row];
+        }
+      }
+      // release this accumulator stage to the MMA issuer (leader CTA's barrier)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&sm.tmem_empty[acc], 0);
+    }
+    if (PASS == 1) {
+      if (half == 1) { sm.xch[0][row] = run_m; sm.xch2[0][row] = run_z; }
+      epi_bar_sync();
+      if (half == 0) {
+        const float om = sm.xch[0][row], oz = sm.xch2[0][row];
+        const float mn = fmaxf(run_m, om);
+        float z = 0.f;
+        if (run_m != -INFINITY) z += run_z * ex2(run_m - mn);
+        if (om != -INFINITY) z += oz * ex2(om - mn);
+        const int tok = (int)rank * 128 + row;
+        part_m[(int64_t)pair * kMaxTokens + tok] = (mn == -INFINITY) ? -INFINITY : mn * kLn2;  // natural-log units
+        part_z[(int64_t)pair * kMaxTokens + tok] = z;
+      }
+    }
+  }
+
+  // ================================ teardown ================================
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, 384] row-major; box = 64 columns (128 B) x 128 rows; SWIZZLE_128B; OOB rows read as 0
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows) {
+  auto enc = get_encode();
+  if (!enc) { set_error("score_tc: cuTensorMapEncodeTiled unavailable"); return SIXDGS_EUNSUPPORTED; }
+  const cuuint64_t dims[2] = {(cuuint64_t)kFeat, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)kFeat * sizeof(__nv_bfloat16)};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("score_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return SIXDGS_ECUDA; }
+  return SIXDGS_OK;
+}
+
+size_t score_tc_workspace() { return (size_t)kMaxTokens * kFeat * sizeof(__nv_bfloat16) + 1024; }
+int score_tc_parts() { return kTcPairs; }
+
+template <int PASS>
+static int launch_tc(const void* kc, int64_t n_rays, const float* q, int n_img, float* pm, float* pz, const float* m,
+                     const float* z, float* scores, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (ws == nullptr || ws_bytes < score_tc_workspace()) { set_error("score_tc: workspace too small"); return SIXDGS_EWORKSPACE; }
+  if ((reinterpret_cast<uintptr_t>(kc) & 15) != 0) { set_error("score_tc: key cache must be 16-byte aligned"); return SIXDGS_EINVAL; }
+  if (n_rays > (int64_t)INT32_MAX - 1024) { set_error("score_tc: n_rays exceeds the TMA coordinate range"); return SIXDGS_EINVAL; }
+  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+  tc_qprep_kernel<<<(kMaxTokens * kFeat + 255) / 256, 256, 0, s>>>(q, n_img, qb);
+  CUtensorMap mk, mq;
+  int rc;
+  if ((rc = make_map(&mk, kc, (uint64_t)n_rays))) return rc;
+  if ((rc = make_map(&mq, qb, kMaxTokens))) return rc;
+  const size_t smem = sizeof(TcSmem) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(score_tc_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("score_tc attr: %s", cudaGetErrorString(e)); return SIXDGS_ECUDA; }
+  score_tc_kernel<PASS><<<kTcPairs * 2, kTcThreads, smem, s>>>(mk, mq, n_rays, n_img, pm, pz, m, z, scores);
+  return check_launch("score_tc");
+}
+
+int score_tc_pass1(const void* kc, int64_t n_rays, const float* q, int n_img, float* pm, float* pz, void* ws,
+                   size_t ws_bytes, cudaStream_t s) {
+  return launch_tc<1>(kc, n_rays, q, n_img, pm, pz, nullptr, nullptr, nullptr, ws, ws_bytes, s);
+}
+int score_tc_pass2(const void* kc, int64_t n_rays, const float* q, int n_img, const float* m, const float* z,
+                   float* scores, void* ws, size_t ws_bytes, cudaStream_t s) {
+  return launch_tc<2>(kc, n_rays, q, n_img, nullptr, nullptr, m, z, scores, ws, ws_bytes, s);
+}
+
 }  // namespace sixdgs

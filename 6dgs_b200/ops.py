@@ -140,12 +140,25 @@ def _kdtype(k: torch.Tensor) -> int:
     raise _lib.SixdgsError(f"key cache must be float32 or bfloat16, got {k.dtype}")
 
 
+_score_ws = {}
+
+
+def _score_workspace(impl: int, device) -> torch.Tensor:
+    """per-(impl, device, stream) scratch for the score kernels (impl 1: bf16 copy of q for the TMA)."""
+    key = (impl, str(device), stream_ptr())
+    if key not in _score_ws:
+        n = int(_lib.load().sixdgs_score_workspace(impl))
+        _score_ws[key] = torch.empty(max(n, 16), dtype=torch.uint8, device=device)
+    return _score_ws[key]
+
+
 def score_pass1(k_cache: torch.Tensor, q: torch.Tensor, impl: int = SCORE_SIMT):
     parts = int(_lib.load().sixdgs_score_parts(impl))
+    ws = _score_workspace(impl, q.device)
     pm = torch.empty(parts, MAX_TOKENS, dtype=torch.float32, device=q.device)
     pz = torch.empty(parts, MAX_TOKENS, dtype=torch.float32, device=q.device)
     call("sixdgs_score_pass1", dptr(k_cache, None), _kdtype(k_cache), k_cache.shape[0], dptr(q), q.shape[0], dptr(pm),
-         dptr(pz), impl, stream_ptr())
+         dptr(pz), impl, dptr(ws, torch.uint8), ws.numel(), stream_ptr())
     return pm, pz
 
 
@@ -161,8 +174,9 @@ def score_pass2(k_cache: torch.Tensor, q: torch.Tensor, m: torch.Tensor, z: torc
     n = k_cache.shape[0]
     scores = out if out is not None else torch.empty(n, dtype=torch.float32, device=q.device)
     amap = torch.empty(q.shape[0], n, dtype=torch.float32, device=q.device) if want_map else None
+    ws = _score_workspace(impl, q.device)
     call("sixdgs_score_pass2", dptr(k_cache, None), _kdtype(k_cache), n, dptr(q), q.shape[0], dptr(m), dptr(z),
-         dptr(scores), dptr(amap), impl, stream_ptr())
+         dptr(scores), dptr(amap), impl, dptr(ws, torch.uint8), ws.numel(), stream_ptr())
     return scores, amap
 
 

@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- pose queries/sec of the 6DGS hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, one rank per GPU
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+
+Workload (config.workload): BASELINE.json configs[2] -- a synthetic 1M-Gaussian scene (every valid
+ellipsoid casts rays, ~29 rays each), one 1080x1920 query image, bf16 key cache scored on the
+tcgen05 path, fp32 LS solve.  A "step" is one pose query: image -> backbone tokens -> q -> two
+streaming passes over the key cache -> top-100 -> fused LS pose tail -> c2w.  Scene preparation
+(ray generation + key cache) is per scene, not per query, and is reported separately.
+
+  value     queries/s, image already resident in HBM, whole query captured in one CUDA graph
+  e2e       queries/s through IdentificationModule.query_pose() from a pinned uint8 HOST image
+            (H2D + /255 + mask inside the timed region) to the 4x4 pose back on the host
+  roofline  ray-score kernels (score_tc pass 1 / pass 2), algorithmic bytes / CUDA-event time / measured HBM peak
+  cpu_baseline  the oracle port (torch CPU, all host threads) on a bounded sample of the same rays,
+            extrapolated linearly in the ray count (per-ray work is independent; stated in `sample`)
+
+N > 1 (torchrun): the selected ellipsoids -- hence rays and key cache -- are sharded in contiguous
+blocks over the ranks (strong scaling: the scene is fixed); per query two tiny NCCL all-gathers
+(softmax statistics [2,256]; top-100 candidates) couple the shards.
+"""
+import argparse
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=1_000_000)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--score-impl", default="tc_bf16", choices=["tc_bf16", "simt_bf16", "simt_fp32"])
+    ap.add_argument("--backbone", default="vits14", choices=["vits14", "synthetic"])
+    ap.add_argument("--cpu-sample-ellipsoids", type=int, default=4000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.gpu = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if "Active" in v and "Not" not in v:
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_query_rate(args, n_rays_total, sample_ellipsoids, threads=None):
+    """Reference algorithm (oracle port) on the host: per query the reference recomputes the ray MLP,
+    the attention over all rays, top-100 and the pose tail (identification_module.py:77-133, test.py:157-198).
+    Timed on `sample_ellipsoids` ellipsoids' rays, extrapolated linearly to n_rays_total."""
+    sx = importlib.import_module("6dgs_b200")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    oracle = importlib.import_module("sixdgs_oracle")
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sc = sx.synthetic.synth_scene(sample_ellipsoids, seed=0, extent=5.0)
+    feats = torch.cat((sc["features_dc"], sc["features_rest"]), 1)
+    t0 = time.perf_counter()
+    # ray generation in 1000-ellipsoid chunks like the reference's cap (per scene, reported separately)
+    parts = []
+    valid = oracle.mask_degraded_ellipsoids(*torch.exp(sc["scaling"]).unbind(-1))
+    nvalid = int(valid.sum())
+    for lo in range(0, min(nvalid, 2000), 1000):
+        idx = torch.arange(lo, min(lo + 1000, nvalid))
+        parts.append(oracle.generate_rays(sc["xyz"], sc["scaling"], sc["rotation"], feats, ellipsoid_idx=idx))
+    t_gen = time.perf_counter() - t0
+    ori = torch.cat([p[0] for p in parts])
+    dirs = torch.cat([p[1] for p in parts])
+    rgb = torch.cat([p[2] for p in parts])
+    gen_rays = ori.shape[0]
+    # tile the generated rays up to the sample size (the per-ray cost does not depend on the values)
+    want = int(sample_ellipsoids * 29)
+    rep = max(1, math.ceil(want / gen_rays))
+    ori, dirs, rgb = ori.repeat(rep, 1)[:want], dirs.repeat(rep, 1)[:want], rgb.repeat(rep, 1)[:want]
+    w = sx.synthetic.synth_id_weights(seed=3)
+    tok = torch.randn(256, 398, generator=torch.Generator().manual_seed(2))
+    up = torch.tensor([0.0, 0.0, 1.0])
+
+    def one_query():
+        cache = {}
+
+        def fea(lo, hi):
+            if (lo, hi) not in cache:  # each chunk's features are computed once per query, as the reference does
+                cache[(lo, hi)] = oracle.ray_features(ori[lo:hi], dirs[lo:hi], rgb[lo:hi], w)
+            return cache[(lo, hi)]
+
+        scores, _, _ = oracle.attention_scores_chunked(tok, fea, ori.shape[0], w, chunk=29000)
+        top = torch.topk(scores, 100)
+        return oracle.pose_tail(top.indices, top.values, ori, dirs, up)[0]
+
+    one_query()
+    ts = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        one_query()
+        ts.append(time.perf_counter() - t0)
+    t_sample = min(ts)
+    per_ray = t_sample / ori.shape[0]
+    t_full = per_ray * n_rays_total
+    return {"value": 1.0 / t_full, "unit": "queries/s", "cores": threads, "kind": "port",
+            "sample": (f"oracle port (torch CPU fp32, {threads} threads): ray MLP + attention + top-100 + pose tail on "
+                       f"{ori.shape[0]} rays in {t_sample:.2f} s/query ({per_ray * 1e6:.2f} us/ray), extrapolated linearly "
+                       f"to {n_rays_total} rays; CPU ray generation {t_gen / max(gen_rays, 1) * 1e6:.1f} us/ray (per scene)"),
+            "s_per_query_sample": t_sample, "us_per_ray": per_ray * 1e6}
+
+
+def expected_rays(n_gaussians):
+    return int(n_gaussians * 29.05)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_rays = expected_rays(args.gaussians)
+    steps = max(1, min(args.steps, 3))
+    base = cpu_query_rate(args, n_rays, args.cpu_sample_ellipsoids)
+    line = {"impl": "reference", "metric": "pose queries/sec, 1M-Gaussian scene", "value": base["value"], "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 / base["value"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, n_rays, None), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, n_rays, n_rays_local):
+    return {"workload": f"{args.gaussians} synthetic Gaussians (all valid ellipsoids, uncapped), {args.height}x{args.width} "
+                        f"image, {args.score_impl} key cache, fp32 LS solve (BASELINE.json configs[2])",
+            "gaussians": args.gaussians, "n_rays": n_rays, "n_rays_per_rank": n_rays_local, "image": [args.height, args.width],
+            "n_img_tokens": 256, "score_impl": args.score_impl, "backbone": args.backbone,
+            "parallelism": f"ray-shard x{args.gpus}", "l2": "inputs larger than L2 (key cache >> 126 MB), no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    sx = importlib.import_module("6dgs_b200")
+    from importlib import import_module
+    sharding = import_module("6dgs_b200.sharding")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    # ---------------- scene preparation (per scene; untimed for the metric, reported) ----------------
+    t0 = time.perf_counter()
+    sc = sx.synthetic.synth_scene(args.gaussians, seed=0, extent=5.0)
+    scene = sx.GaussianScene.from_dict(sc, device=dev)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    ori, dirs, rgb = sx.generate_all_possible_rays(scene, max_ellipsoids=None, shard=(rank, world) if world > 1 else None)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    backbone = sx.synthetic.SyntheticBackbone() if args.backbone == "synthetic" else sx.DinoV2ViTS14()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(0)
+        idm = sx.IdentificationModule("dino", backbone=backbone, score_impl=args.score_impl)
+    idm.load_state_dict(sx.synthetic.synth_id_weights(seed=3), strict=False)
+    idm = idm.to(dev).eval().requires_grad_(False)
+    cache = idm.build_key_cache(ori, dirs, rgb)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    n_local = ori.shape[0]
+    n_total = n_local
+    if world > 1:
+        t = torch.tensor([n_local], device=dev, dtype=torch.long)
+        dist.all_reduce(t)
+        n_total = int(t.item())
+    est = sharding.ShardedPoseEstimator(idm, ori, dirs, cache, rank, world)
+
+    img_u8 = (sx.synthetic.synth_image(args.height, args.width, seed=7) * 255).to(torch.uint8)
+    img_host = img_u8.pin_memory()
+    img_dev = (img_u8.to(dev).float() / 255.0).contiguous()
+    mask_dev = torch.ones(args.height, args.width, dtype=torch.bool, device=dev)
+
+    def query():
+        return est.query(img_dev, mask_dev)
+
+    # ---------------- warm-up, optional CUDA graph ----------------
+    for _ in range(max(args.warmup, 3)):
+        c2w, aux = query()
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph and world == 1:
+        try:
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    query()
+            torch.cuda.current_stream().wait_stream(s)
+            with torch.cuda.graph(g):
+                g_out = query()
+            g.replay()
+            torch.cuda.synchronize()
+            if torch.allclose(g_out[0], c2w, atol=1e-5, equal_nan=True):
+                graph = g
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            query()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- timed region: `value` ----------------
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = args.steps / (ms / 1e3)
+
+    # ---------------- e2e: host image -> pose on host, through the public API ----------------
+    pose_host = torch.empty(4, 4).pin_memory()
+
+    def e2e_step():
+        d = img_host.to(dev, non_blocking=True)
+        img = d.float() / 255.0
+        m = torch.ones_like(img[..., 0], dtype=torch.bool)
+        c, _ = est.query(img, m)
+        pose_host.copy_(c, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    barrier()
+    t0e = time.perf_counter()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ee1.record()
+    barrier()
+    e2e_ms = max(ee0.elapsed_time(ee1), (time.perf_counter() - t0e) * 1e3 * 0.0)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": args.steps / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": int(img_host.numel()),
+           "d2h_bytes_per_step": 64, "ms_per_step": e2e_ms / args.steps}
+
+    # ---------------- roofline of the ray-score kernels (CUDA events around each launch) ----------------
+    peak, peak_src = load_peaks()
+    impl = idm._impl
+    tok = torch.randn(256, 398, device=dev)
+    q = sx.ops.project_queries(tok, idm.packed_weights())
+    p1, p2 = [], []
+    for i in range(3 + 10):
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        pm, pz = sx.ops.score_pass1(cache.keys, q, impl)
+        b.record()
+        m_, z_ = sx.ops.score_merge(pm, pz, 256)
+        b2 = torch.cuda.Event(enable_timing=True)
+        b2.record()
+        sx.ops.score_pass2(cache.keys, q, m_, z_, impl, out=cache.scores)
+        c.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            p1.append(a.elapsed_time(b))
+            p2.append(b2.elapsed_time(c))
+    kbytes = cache.keys.element_size() * 384
+    t1_ms, t2_ms = sum(p1) / len(p1), sum(p2) / len(p2)
+    bytes1 = n_local * kbytes + est.parts * 2 * 256 * 4
+    bytes2 = n_local * kbytes + n_local * 4
+    ach1, ach2 = bytes1 / (t1_ms * 1e-3) / 1e9, bytes2 / (t2_ms * 1e-3) / 1e9
+    dom = ("score_pass1", ach1, t1_ms, bytes1) if t1_ms >= t2_ms else ("score_pass2", ach2, t2_ms, bytes2)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom[0])
+    roofline = {"bound": "hbm", "kernel": f"score_tc_kernel<{1 if dom[0] == 'score_pass1' else 2}> ({dom[0]})",
+                "achieved": dom[1], "peak": peak, "unit": "GB/s", "frac": dom[1] / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[3], "ms_per_launch": dom[2],
+                "detail": {"pass1": {"ms": t1_ms, "GBps": ach1, "frac": ach1 / peak},
+                           "pass2": {"ms": t2_ms, "GBps": ach2, "frac": ach2 / peak},
+                           "flops_per_launch": 2.0 * 256 * 384 * n_local,
+                           "tflops_pass2": 2.0 * 256 * 384 * n_local / (t2_ms * 1e-3) / 1e12}}
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_query_rate(args, n_total, args.cpu_sample_ellipsoids)
+
+    if rank == 0:
+        line = {"metric": "pose queries/sec, 1M-Gaussian scene", "value": value, "unit": "queries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if "bf16" in args.score_impl else "f32",
+                "data": "synthetic", "config": workload_config(args, n_total, n_local), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": est.launches_per_query * args.steps, "cuda_graph": graph is not None,
+                "roofline": roofline, "cpu_baseline": cpu,
+                "prepare": {"scene_to_gpu_s": t1 - t0, "raygen_s": t2 - t1, "key_cache_s": t3 - t2,
+                            "rays_per_s_raygen": n_local / max(t2 - t1, 1e-9)},
+                "pose": {"centre": [float(x) for x in c2w[:3, 3].tolist()], "status": int(aux[7].item())}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

