@@ -139,15 +139,30 @@ pose_tail_kernel(const float* __restrict__ rays_ori, const float* __restrict__ r
     once[i] = (cnt == 1);
   }
   __syncthreads();
-  // torch.isin(rows, unique_once).any(dim=1): ELEMENT-wise membership of any coordinate in the
-  // flattened set of once-only rows (reference quirk, test.py:158-160)
+  // mask = torch.isin(rows, unique_once_rows, assume_unique=True).any(dim=1)             test.py:158-160
+  // Reference quirk, reproduced: isin works ELEMENT-wise on the flattened coordinates, and with
+  // assume_unique=True torch takes its sort-based path (stable sort of [elements ; test_elements],
+  // flag = "next sorted entry is equal") whenever test.numel() >= 10 * elements.numel()^0.145
+  // (ATen TensorCompare.cpp isin_Tensor_Tensor_out).  A coordinate is therefore flagged iff an equal
+  // value occurs LATER in the concatenation: in a later flattened position of the rows themselves, or
+  // anywhere in the once-only rows.  Net effect on duplicated origins: the first copy survives, later
+  // copies are dropped.  With very few once-only rows torch uses plain membership instead.
+  __shared__ int s_once;
+  if (t == 0) {
+    int c = 0;
+    for (int i = 0; i < k; ++i) c += once[i];
+    s_once = c;
+  }
+  __syncthreads();
+  const bool sorting_path = (float)(3 * s_once) >= 10.0f * powf((float)(3 * k), 0.145f);
   for (int i = t; i < k; i += blockDim.x) {
-    bool kp = once[i];
-    for (int j = 0; j < k && !kp; ++j) {
-      if (!once[j]) continue;
-      for (int a = 0; a < 3 && !kp; ++a)
+    bool kp = false;
+    for (int a = 0; a < 3 && !kp; ++a) {
+      const float v = so[i][a];
+      const int f = 3 * i + a;
+      for (int j = 0; j < k && !kp; ++j)
         for (int b = 0; b < 3; ++b)
-          if (so[i][a] == so[j][b]) { kp = true; break; }
+          if (so[j][b] == v && (once[j] || (sorting_path && (3 * j + b) > f))) { kp = true; break; }
     }
     keep[i] = kp;
   }

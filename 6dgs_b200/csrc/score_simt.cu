@@ -120,7 +120,8 @@ score_simt_kernel(const TK* __restrict__ kc, int64_t n_rays, const float* __rest
 
 // log-sum-exp merge of partial (max, sum-exp) rows; also merges the rows gathered from other ranks
 __global__ void score_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_z, int n_parts,
-                                   int n_img, float* __restrict__ m, float* __restrict__ z) {
+                                   int n_img, const uint8_t* __restrict__ token_valid, float* __restrict__ m,
+                                   float* __restrict__ z) {
   const int t = threadIdx.x;
   if (t >= kMaxTokens) return;
   float mx = -INFINITY;
@@ -130,8 +131,10 @@ __global__ void score_merge_kernel(const float* __restrict__ part_m, const float
     const float pm = part_m[(int64_t)p * kMaxTokens + t];
     if (pm != -INFINITY) acc += (double)part_z[(int64_t)p * kMaxTokens + t] * (double)expf(pm - mx);
   }
-  m[t] = (t < n_img) ? mx : 0.f;
-  z[t] = (t < n_img) ? (float)acc : 1.f;
+  // masked-out tokens get (m, z) = (+inf, +inf): exp(L - inf) / inf == 0 in pass 2 whatever L is
+  const bool live = (t < n_img) && (token_valid == nullptr || token_valid[t] != 0);
+  m[t] = live ? mx : INFINITY;
+  z[t] = live ? (float)acc : INFINITY;
 }
 
 template <typename TK>
@@ -171,10 +174,10 @@ int score_simt_parts() { return kSimtParts; }
 
 using namespace sixdgs;
 
-extern "C" int sixdgs_score_merge(const float* part_m, const float* part_z, int n_parts, int n_img, float* m,
-                                  float* z, void* stream) {
+extern "C" int sixdgs_score_merge(const float* part_m, const float* part_z, int n_parts, int n_img,
+                                  const uint8_t* token_valid, float* m, float* z, void* stream) {
   SIXDGS_REQUIRE(part_m && part_z && m && z, "null pointer");
   SIXDGS_REQUIRE(n_parts > 0 && n_img > 0 && n_img <= kMaxTokens, "bad size");
-  score_merge_kernel<<<1, kMaxTokens, 0, (cudaStream_t)stream>>>(part_m, part_z, n_parts, n_img, m, z);
+  score_merge_kernel<<<1, kMaxTokens, 0, (cudaStream_t)stream>>>(part_m, part_z, n_parts, n_img, token_valid, m, z);
   return check_launch("score_merge");
 }

@@ -300,7 +300,29 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constan
           float(&nxt)[32] = (c & 1) ? va : vb;
           if (c + 1 < 4) tmem_ld32(taddr + (c + 1) * 32, nxt);
           const int nv = valid - c * 32;  // columns of this chunk that are real rays
-          if (nv > 0) {
+          if (nv >= 32) {
+            // full chunk (every tile but the last): 4 independent max / sum chains
+            float m0 = fmaxf(cur[0], cur[1]), m1 = fmaxf(cur[2], cur[3]), m2 = fmaxf(cur[4], cur[5]),
+                  m3 = fmaxf(cur[6], cur[7]);
+#pragma unroll
+            for (int j = 8; j < 32; j += 8) {
+              m0 = fmaxf(m0, fmaxf(cur[j + 0], cur[j + 1]));
+              m1 = fmaxf(m1, fmaxf(cur[j + 2], cur[j + 3]));
+              m2 = fmaxf(m2, fmaxf(cur[j + 4], cur[j + 5]));
+              m3 = fmaxf(m3, fmaxf(cur[j + 6], cur[j + 7]));
+            }
+            const float mn = fmaxf(fmaxf(run_m, fmaxf(m0, m1)), fmaxf(m2, m3));
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              s0 += ex2(cur[j + 0] - mn);
+              s1 += ex2(cur[j + 1] - mn);
+              s2 += ex2(cur[j + 2] - mn);
+              s3 += ex2(cur[j + 3] - mn);
+            }
+            run_z = run_z * ex2(run_m - mn) + ((s0 + s1) + (s2 + s3));
+            run_m = mn;
+          } else if (nv > 0) {
             float cm = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (j < nv) ? cur[j] : -INFINITY);
@@ -314,7 +336,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constan
           if (c + 1 < 4) tmem_ld_wait(nxt);
         }
       } else {
-        float s = 0.f;
+        float s = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         tmem_ld32(taddr, va);
         tmem_ld_wait(va);
 #pragma unroll
@@ -327,12 +349,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constan
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 c4 = cc[j4];
             s += ex2(cur[j4 * 4 + 0] - c4.x);
-            s += ex2(cur[j4 * 4 + 1] - c4.y);
-            s += ex2(cur[j4 * 4 + 2] - c4.z);
-            s += ex2(cur[j4 * 4 + 3] - c4.w);
+            s1 += ex2(cur[j4 * 4 + 1] - c4.y);
+            s2 += ex2(cur[j4 * 4 + 2] - c4.z);
+            s3 += ex2(cur[j4 * 4 + 3] - c4.w);
           }
           if (c + 1 < 4) tmem_ld_wait(nxt);
         }
+        s = (s + s1) + (s2 + s3);
         // combine the two column halves of each ray, then one coalesced 128-float store per CTA
         if (half == 1) sm.xch[acc][row] = s;
         epi_bar_sync();

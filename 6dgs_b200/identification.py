@@ -178,7 +178,10 @@ class IdentificationModule(torch.nn.Module):
         return scores, amap, (m, z)
 
     def _camera_up(self, grid: torch.Tensor) -> torch.Tensor:
-        return torch.nn.functional.normalize(self.camera_direction_prediction_network(grid), dim=-1)
+        # full-fp32 convolutions: cuDNN's default TF32 path moves the up vector by ~1e-3, which is more
+        # than the 1e-4 pose tolerance (the head is 1.65 GFLOP -- negligible either way)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return torch.nn.functional.normalize(self.camera_direction_prediction_network(grid), dim=-1)
 
     def run_attention(self, img, mask, rays_ori, rays_dir, rays_rgb):
         """-> (score[n], attention_map[n_img,n] or None, features_img_flat[n_img,384], camera_up_dir[3])
@@ -216,8 +219,11 @@ class IdentificationModule(torch.nn.Module):
         """Fused query: image -> c2w[4,4] with no host synchronisation (test.py:85-198 in six launches
         + backbone + up head).  Returns (c2w, aux) with aux = [centre3, watch3, n_kept, status]."""
         cache = cache or self._cache_for(rays_ori, rays_dir, rays_rgb)
-        tok_pe, _, grid = self.backbone_wrapper(img, mask)
-        scores, _, _ = self.score_tokens(tok_pe, cache)
+        tok_pe, tok, keep = self.backbone_wrapper.tokens_dense(img, mask)
+        q = ops.project_queries(tok_pe.reshape(-1, tok_pe.shape[-1]).contiguous(), self.packed_weights())
+        pm, pz = ops.score_pass1(cache.keys, q, self._impl)
+        m, z = ops.score_merge(pm, pz, q.shape[0], keep.reshape(-1).to(torch.uint8))
+        scores, _ = ops.score_pass2(cache.keys, q, m, z, self._impl)
         vals, idx = ops.topk(scores, rays_to_output)
-        up = self._camera_up(grid)
+        up = self._camera_up(tok.permute(2, 0, 1))
         return ops.pose_tail(rays_ori, rays_dir, idx, vals, up)

@@ -117,16 +117,22 @@ class BackboneWrapper(torch.nn.Module):
         """[x, y, sin(x*2^f) sin(y*2^f) (coordinate-major), cos(...)] on linspace(-1,1) (backbone.py:116-139)."""
         axes = [torch.linspace(-1.0, 1.0, steps=s, dtype=dtype, device=device) for s in shape]
         pos = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, len(shape))
-        bands = (2 ** torch.arange(freqs).float()).to(pos.device)
+        bands = 2.0 ** torch.arange(freqs, dtype=dtype, device=pos.device)
         ang = (pos[..., None] * bands).reshape(pos.shape[0], -1)
         return torch.cat([pos, torch.sin(ang), torch.cos(ang)], dim=-1).reshape(*shape, -1)
 
-    def forward(self, img: torch.Tensor, mask: torch.Tensor):
-        """img [H,W,3] in [0,1], mask [H,W] bool -> (tokens+pe [n_img,398], tokens [n_img,384], grid [384,16,16])."""
+    def tokens_dense(self, img: torch.Tensor, mask: torch.Tensor):
+        """All 256 grid tokens plus their validity, no host synchronisation:
+        -> (tokens+pe [256,398], tokens [16,16,384], keep [16,16] bool)."""
         x = self.transformations(img[None].permute(0, 3, 1, 2))
         keep = self.mask_transformations(mask[None, None] * 1.0)[0, 0] > 0.1
         gh, gw = self.backbone_wh
         tok = self.image_preprocessing_net.forward_features(x)["x_norm_patchtokens"][0].reshape(gh, gw, self.img_num_features)
         pe = self.get_img_position_encoding((gh, gw), 3, dtype=img.dtype, device=img.device)
-        tok_pe = torch.cat((tok, pe), dim=-1)
+        return torch.cat((tok, pe), dim=-1), tok, keep
+
+    def forward(self, img: torch.Tensor, mask: torch.Tensor):
+        """img [H,W,3] in [0,1], mask [H,W] bool -> (tokens+pe [n_img,398], tokens [n_img,384], grid [384,16,16]).
+        Boolean-mask compaction like the reference (backbone.py:110-114): one host sync on n_img."""
+        tok_pe, tok, keep = self.tokens_dense(img, mask)
         return tok_pe[keep].view(-1, tok_pe.shape[-1]), tok[keep].view(-1, tok.shape[-1]), tok.permute(2, 0, 1)

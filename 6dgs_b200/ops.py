@@ -162,10 +162,11 @@ def score_pass1(k_cache: torch.Tensor, q: torch.Tensor, impl: int = SCORE_SIMT):
     return pm, pz
 
 
-def score_merge(pm: torch.Tensor, pz: torch.Tensor, n_img: int):
+def score_merge(pm: torch.Tensor, pz: torch.Tensor, n_img: int, token_valid: Optional[torch.Tensor] = None):
     m = torch.empty(MAX_TOKENS, dtype=torch.float32, device=pm.device)
     z = torch.empty(MAX_TOKENS, dtype=torch.float32, device=pm.device)
-    call("sixdgs_score_merge", dptr(pm), dptr(pz), pm.shape[0], n_img, dptr(m), dptr(z), stream_ptr())
+    call("sixdgs_score_merge", dptr(pm), dptr(pz), pm.shape[0], n_img, dptr(token_valid, torch.uint8), dptr(m), dptr(z),
+         stream_ptr())
     return m, z
 
 

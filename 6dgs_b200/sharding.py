@@ -29,8 +29,9 @@ class CudaBackend:
         self.parts = int(_lib.load().sixdgs_score_parts(self.impl))
 
     def tokens(self, img, mask):
-        tok_pe, _, grid = self.idm.backbone_wrapper(img, mask)
-        return tok_pe, grid
+        """dense tokens: all 256 grid tokens + validity bytes, so a masked query needs no host sync"""
+        tok_pe, tok, keep = self.idm.backbone_wrapper.tokens_dense(img, mask)
+        return tok_pe.reshape(-1, tok_pe.shape[-1]).contiguous(), tok.permute(2, 0, 1), keep.reshape(-1).to(torch.uint8)
 
     def project(self, tok_pe):
         return ops.project_queries(tok_pe, self.idm.packed_weights())
@@ -38,8 +39,8 @@ class CudaBackend:
     def pass1(self, keys, q):
         return ops.score_pass1(keys, q, self.impl)
 
-    def merge(self, pm, pz, n_img):
-        return ops.score_merge(pm, pz, n_img)
+    def merge(self, pm, pz, n_img, valid=None):
+        return ops.score_merge(pm, pz, n_img, valid)
 
     def pass2(self, keys, q, m, z, out):
         return ops.score_pass2(keys, q, m, z, self.impl, out=out)[0]
@@ -78,13 +79,13 @@ class ShardedPoseEstimator:
     def query(self, img: torch.Tensor, mask: torch.Tensor, k: int = 100):
         """-> (c2w[4,4], aux[8]); identical on every rank."""
         b = self.backend
-        tok_pe, grid = b.tokens(img, mask)
+        tok_pe, grid, valid = b.tokens(img, mask)
         n_img = tok_pe.shape[0]
         q = b.project(tok_pe)
         pm, pz = b.pass1(self.cache.keys, q)
         if self.world > 1:
             pm, pz = self._all_gather(pm), self._all_gather(pz)
-        m, z = b.merge(pm, pz, n_img)
+        m, z = b.merge(pm, pz, n_img, valid)
         scores = b.pass2(self.cache.keys, q, m, z, self.cache.scores)
         k_local = min(k, self.cache.n_rays)
         vals, idx = b.topk(scores, k_local)

@@ -110,7 +110,9 @@ int sixdgs_linear(const float* x, int64_t m, int k, int lda, const float* w, con
  * q[n_img,384] fp32 (already projected), K cache [n_rays,384] in k_dtype.
  * pass1: per-token running (max, sum-exp) of logits q.k/sqrt(384) over this K shard, written as
  *        `n_parts` partial rows part_m/part_z[n_parts, 256] (n_parts = sixdgs_score_parts()).
- * merge: log-sum-exp merge of partial rows (also used across ranks after an all-gather) -> m,z[256].
+ * merge: log-sum-exp merge of partial rows (also used across ranks after an all-gather) -> m,z[256];
+ *        tokens >= n_img or with token_valid == 0 get (m, z) = (+inf, +inf) so that pass 2 ignores them
+ *        (lets a masked query run on all 256 grid tokens without a host-side compaction / sync).
  * pass2: scores[r] = sum_i exp(L_ir - m_i) / z_i; attn_map (nullable) [n_img, n_rays].
  * impl: 0 = SIMT fp32 (exact path), 1 = tcgen05 bf16 tensor cores (K must be bf16). */
 int sixdgs_score_parts(int impl);
@@ -119,7 +121,8 @@ size_t sixdgs_score_workspace(int impl);
 int sixdgs_score_pass1(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_img,
                        float* part_m, float* part_z, int impl, void* workspace, size_t workspace_bytes,
                        void* stream);
-int sixdgs_score_merge(const float* part_m, const float* part_z, int n_parts, int n_img, float* m,
+int sixdgs_score_merge(const float* part_m, const float* part_z, int n_parts, int n_img,
+                       const uint8_t* token_valid /* nullable [256]: 0 = token masked out */, float* m,
                        float* z, void* stream);
 int sixdgs_score_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_img,
                        const float* m, const float* z, float* scores, float* attn_map, int impl,

@@ -443,7 +443,8 @@ def make_rotation_mat(direction, up):
 
 
 def pose_tail(idx, weights, rays_ori, rays_dir, camera_up) -> Tuple[torch.Tensor, dict]:
-    """top-k rays -> c2w[4,4] (test.py:157-198): drop rays whose origin is repeated, unweighted LS,
+    """top-k rays -> c2w[4,4] (test.py:157-198): drop repeated origins (torch.isin(..., assume_unique=True)
+    is element-wise and sort-based, so the FIRST copy of a repeated origin survives), unweighted LS,
     exclude negatives, LS again (still unweighted), watch = norm(sum w d), rotation from
     (-watch, up); singular rotation -> identity."""
     o = rays_ori[idx]

@@ -29,7 +29,7 @@ class OracleBackend:
         self.o, self.w, self.tok_pe, self.up = oracle, weights, tok_pe, up
 
     def tokens(self, img, mask):
-        return self.tok_pe, None
+        return self.tok_pe, None, None
 
     def project(self, tok_pe):
         return torch.nn.functional.linear(tok_pe, self.w["attention.q_proj.weight"], self.w["attention.q_proj.bias"])
@@ -41,7 +41,7 @@ class OracleBackend:
         pad = 256 - m.shape[0]
         return (torch.cat((m, torch.full((pad,), -float("inf"))))[None], torch.cat((z, torch.zeros(pad)))[None])
 
-    def merge(self, pm, pz, n_img):
+    def merge(self, pm, pz, n_img, valid=None):
         m = pm.max(0).values
         z = (pz * torch.exp(pm - m[None])).nan_to_num(0.0).sum(0)
         return m[:n_img], z[:n_img]
