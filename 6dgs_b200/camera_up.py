@@ -22,6 +22,19 @@ class CameraDirectionPredictor(torch.nn.Module):
         self.mlp = torch.nn.Sequential(torch.nn.Linear(self.in_mlpC, featureC), torch.nn.ReLU(inplace=True),
                                        torch.nn.Linear(featureC, fea_output))
 
+    @staticmethod
+    def _conv_gemm(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
+        """valid convolution as im2col + one fp32 GEMM.  cuDNN's heuristics pick Winograd/FFT style
+        algorithms for these 384-channel 5x5 layers whose results differ from the fp32 direct sum by ~2e-4
+        relative -- more than the 1e-4 pose tolerance once it reaches the rotation; a plain GEMM does not."""
+        k = conv.kernel_size[0]
+        cols = torch.nn.functional.unfold(x, k)  # [1, C*k*k, L]
+        out = conv.weight.view(conv.out_channels, -1) @ cols[0] + conv.bias[:, None]
+        side = x.shape[-1] - k + 1
+        return out.view(1, conv.out_channels, side, side)
+
     def forward(self, image_features: torch.Tensor) -> torch.Tensor:
-        y = self.dim_reducer2(self.dim_reducer1(image_features[None]))
+        y = image_features[None]
+        for conv in (self.dim_reducer1[0], self.dim_reducer1[2], self.dim_reducer1[4], self.dim_reducer2[0]):
+            y = torch.relu(self._conv_gemm(y, conv))
         return self.mlp(y.view(y.shape[0], -1))[0]

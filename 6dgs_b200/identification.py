@@ -178,10 +178,7 @@ class IdentificationModule(torch.nn.Module):
         return scores, amap, (m, z)
 
     def _camera_up(self, grid: torch.Tensor) -> torch.Tensor:
-        # full-fp32 convolutions: cuDNN's default TF32 path moves the up vector by ~1e-3, which is more
-        # than the 1e-4 pose tolerance (the head is 1.65 GFLOP -- negligible either way)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            return torch.nn.functional.normalize(self.camera_direction_prediction_network(grid), dim=-1)
+        return torch.nn.functional.normalize(self.camera_direction_prediction_network(grid), dim=-1)
 
     def run_attention(self, img, mask, rays_ori, rays_dir, rays_rgb):
         """-> (score[n], attention_map[n_img,n] or None, features_img_flat[n_img,384], camera_up_dir[3])

@@ -105,9 +105,11 @@ class BackboneWrapper(torch.nn.Module):
         self.norm_mean = torch.nn.Parameter(torch.tensor(IMAGENET_MEAN, dtype=torch.float32), requires_grad=False)
         self.norm_std = torch.nn.Parameter(torch.tensor(IMAGENET_STD, dtype=torch.float32), requires_grad=False)
         bicubic, bilinear = transforms.InterpolationMode.BICUBIC, transforms.InterpolationMode.BILINEAR
+        # Normalize is applied with the registered norm_mean/norm_std parameters: torchvision's Normalize
+        # builds its mean/std tensors from Python tuples on every call (a pageable H2D copy, which also
+        # cannot be captured in a CUDA graph)
         self.transformations = transforms.Compose([
-            transforms.Resize(256, interpolation=bicubic, antialias=True), transforms.CenterCrop(224),
-            transforms.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD)])
+            transforms.Resize(256, interpolation=bicubic, antialias=True), transforms.CenterCrop(224)])
         self.mask_transformations = transforms.Compose([
             transforms.Resize(256, interpolation=bilinear, antialias=True), transforms.CenterCrop(224),
             transforms.Resize(self.backbone_wh[0], interpolation=bilinear, antialias=True)])
@@ -125,6 +127,7 @@ class BackboneWrapper(torch.nn.Module):
         """All 256 grid tokens plus their validity, no host synchronisation:
         -> (tokens+pe [256,398], tokens [16,16,384], keep [16,16] bool)."""
         x = self.transformations(img[None].permute(0, 3, 1, 2))
+        x = (x - self.norm_mean.view(1, 3, 1, 1)) / self.norm_std.view(1, 3, 1, 1)
         keep = self.mask_transformations(mask[None, None] * 1.0)[0, 0] > 0.1
         gh, gw = self.backbone_wh
         tok = self.image_preprocessing_net.forward_features(x)["x_norm_patchtokens"][0].reshape(gh, gw, self.img_num_features)

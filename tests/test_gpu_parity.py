@@ -106,14 +106,23 @@ def test_generate_rays_vs_reference(sx):
     assert (rgb >= 0).all()
 
 
-def test_generate_rays_capped_and_properties(sx, synthetic):
+def test_generate_rays_capped_and_properties(sx, synthetic, oracle):
     g = load_golden("rays_capped.npz")
     sc = synthetic.synth_scene(g["scene_n"], seed=g["scene_seed"])
     scene = sx.GaussianScene.from_dict(sc, device=DEV)
     ori, dirs, rgb, gid = sx.generate_all_possible_rays(scene, ellipsoid_idx=g["perm"], return_ids=True)
     assert abs(ori.shape[0] - g["n_rays"]) <= 0.002 * g["n_rays"]
     sums = torch.stack((ori.double().sum(0), dirs.double().sum(0), rgb.double().sum(0))).cpu()
-    assert torch.allclose(sums, g["sums"], rtol=2e-3, atol=0.5)
+    assert torch.allclose(sums, g["sums"], rtol=2e-3, atol=0.002 * g["n_rays"])  # up to 0.2 % of the rays may differ
+    # per-ellipsoid ray counts against the oracle on the same selection: a near-degenerate kNN covariance can
+    # flip a normal (and with it one ellipsoid's hemisphere), nothing else may differ
+    o_ori, _, _, aux = oracle.generate_rays(sc["xyz"], sc["scaling"], sc["rotation"],
+                                            torch.cat((sc["features_dc"], sc["features_rest"]), 1),
+                                            ellipsoid_idx=g["perm"], return_aux=True)
+    cnt_ref = torch.bincount(aux["gid"], minlength=g["scene_n"])
+    cnt = torch.bincount(gid.cpu(), minlength=g["scene_n"])
+    assert (cnt == cnt_ref).float().mean().item() >= 0.99
+    assert (cnt.bool() == cnt_ref.bool()).all()
     # every origin lies on its ellipsoid: |S^-1 R^T (o - mu)| == 1
     q = torch.nn.functional.normalize(scene._rotation[gid])
     w, x, y, z = q.unbind(-1)
