@@ -61,14 +61,23 @@ class DinoV2ViTS14(torch.nn.Module):
         self.blocks = torch.nn.ModuleList([_Block(dim, heads) for _ in range(depth)])
         self.norm = torch.nn.LayerNorm(dim, eps=1e-6)
         self.base_grid = base_grid
+        self._pos_cache = None
 
     def _pos(self, gh, gw):
-        cls, grid = self.pos_embed[:, :1], self.pos_embed[:, 1:]
         if gh == self.base_grid and gw == self.base_grid:
             return self.pos_embed
-        g = grid.reshape(1, self.base_grid, self.base_grid, -1).permute(0, 3, 1, 2)
-        g = F.interpolate(g, size=(gh, gw), mode="bicubic", align_corners=False)
-        return torch.cat((cls, g.permute(0, 2, 3, 1).reshape(1, gh * gw, -1)), 1)
+        # the 37x37 -> 16x16 bicubic resample of the position table only depends on the weights: cache it
+        # (torch runs this interpolate as a single 1024-thread block, ~1 ms per call on B200)
+        key = (gh, gw, self.pos_embed.data_ptr(), self.pos_embed._version, self.pos_embed.device)
+        if self._pos_cache is None or self._pos_cache[0] != key or torch.is_grad_enabled() and self.pos_embed.requires_grad:
+            cls, grid = self.pos_embed[:, :1], self.pos_embed[:, 1:]
+            g = grid.reshape(1, self.base_grid, self.base_grid, -1).permute(0, 3, 1, 2)
+            g = F.interpolate(g, size=(gh, gw), mode="bicubic", align_corners=False)
+            pos = torch.cat((cls, g.permute(0, 2, 3, 1).reshape(1, gh * gw, -1)), 1)
+            if torch.is_grad_enabled() and self.pos_embed.requires_grad:
+                return pos
+            self._pos_cache = (key, pos.detach())
+        return self._pos_cache[1]
 
     def forward_features(self, x):
         t = self.patch_embed.proj(x)

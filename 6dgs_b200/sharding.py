@@ -71,8 +71,13 @@ class ShardedPoseEstimator:
     def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
         import torch.distributed as dist
 
+        t = t.contiguous()
+        if dist.get_backend(self.group) == "nccl":  # one collective kernel, no per-rank copies
+            out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(out, t, group=self.group)
+            return out
         outs = [torch.empty_like(t) for _ in range(self.world)]
-        dist.all_gather(outs, t.contiguous(), group=self.group)
+        dist.all_gather(outs, t, group=self.group)
         return torch.cat(outs, 0)
 
     @torch.no_grad()

@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--score-impl", default="tc_bf16", choices=["tc_bf16", "simt_bf16", "simt_fp32"])
     ap.add_argument("--backbone", default="vits14", choices=["vits14", "synthetic"])
+    ap.add_argument("--backbone-matmul", default="tf32", choices=["fp32", "tf32"],
+                    help="precision of the torch matmuls inside the ViT backbone / camera-up head (boundary "
+                         "components, PyTorch): tf32 = torch.set_float32_matmul_precision('high')")
     ap.add_argument("--cpu-sample-ellipsoids", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -206,7 +209,7 @@ def workload_config(args, n_rays, n_rays_local):
     return {"workload": f"{args.gaussians} synthetic Gaussians (all valid ellipsoids, uncapped), {args.height}x{args.width} "
                         f"image, {args.score_impl} key cache, fp32 LS solve (BASELINE.json configs[2])",
             "gaussians": args.gaussians, "n_rays": n_rays, "n_rays_per_rank": n_rays_local, "image": [args.height, args.width],
-            "n_img_tokens": 256, "score_impl": args.score_impl, "backbone": args.backbone,
+            "n_img_tokens": 256, "score_impl": args.score_impl, "backbone": args.backbone, "backbone_matmul": args.backbone_matmul,
             "parallelism": f"ray-shard x{args.gpus}", "l2": "inputs larger than L2 (key cache >> 126 MB), no flush needed"}
 
 
@@ -225,6 +228,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.backbone_matmul == "tf32":
+        torch.set_float32_matmul_precision("high")
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
