@@ -276,7 +276,7 @@ def main():
         c2w, aux = query()
     torch.cuda.synchronize()
     graph = None
-    if not args.no_graph and world == 1:
+    if not args.no_graph:
         try:
             g = torch.cuda.CUDAGraph()
             s = torch.cuda.Stream()
@@ -291,6 +291,8 @@ def main():
             torch.cuda.synchronize()
             if torch.allclose(g_out[0], c2w, atol=1e-5, equal_nan=True):
                 graph = g
+            else:
+                print("[bench] CUDA graph replay does not reproduce the eager pose; timing eager launches", file=sys.stderr)
         except Exception as e:  # noqa: BLE001
             print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
             graph = None
