@@ -19,6 +19,7 @@ SOURCES = {
     "raygen.cu": ["-fmad=false"],
     "normals.cu": ["-fmad=false"],
     "features.cu": [],
+    "features_tc.cu": [],
     "score_simt.cu": [],
     "score_tc.cu": [],
     "topk.cu": [],

@@ -6,8 +6,9 @@
 // -- the key cache K[n_rays, 384] in fp32 or bf16 -- is what the per-query score kernels stream.
 //
 // Layout of the per-chunk workspace (fp32, row-major, chunk = kChunk rays):
-//   X  [chunk, 656] : cols 0..511 = second hidden layer h, cols 512..652 = the 141-wide MLP input
-//                     (9 raw + PE), cols 653..655 = 0  -> the concat [h, x] of mlp2 is free
+//   X  [chunk, 672] : cols 0..511 = second hidden layer h, cols 512..652 = the 141-wide MLP input
+//                     (9 raw + PE), cols 653..671 = 0  -> the concat [h, x] of mlp2 is free
+//                     (672 = 512 + 160: every reduction dim is a multiple of 32 for the TF32 UMMA k-blocks)
 //   H  [chunk, 512] : first hidden layer, later the third hidden layer
 //   F  [chunk, 384] : ray feature (output of mlp2) when a projection follows
 #include "common.cuh"
@@ -16,7 +17,8 @@
 namespace sixdgs {
 
 constexpr int kChunk = 1 << 17;  // rays per workspace chunk
-constexpr int kXW = 656;         // padded concat width (512 + 141 -> 656)
+constexpr int kXW = 672;         // padded concat width (512 + 141 -> 672)
+constexpr int kInPad = 160;      // padded MLP input width (141 -> 160)
 constexpr int kIn = 141;
 
 // x = [ori3, dir3, rgb3, sin(ori*2^f) (coordinate-major, f=0..7), cos(..), sin(dir*2^f), cos(..),
@@ -43,7 +45,8 @@ __global__ void pe_kernel(const float* __restrict__ ori, const float* __restrict
       }
     o += 6 * nf;
   }
-  x[141] = 0.f; x[142] = 0.f; x[143] = 0.f;
+#pragma unroll
+  for (int i = kIn; i < kInPad; ++i) x[i] = 0.f;
 }
 
 template <typename TO>
@@ -89,6 +92,18 @@ static int launch_linear(const float* x, int64_t m, int k, int64_t lda, const fl
   return check_launch("linear");
 }
 
+// tensor-core (TF32 tcgen05) GEMM, features_tc.cu
+template <typename TO>
+int launch_linear_tc(const float* x, int64_t m, int k, int64_t lda, const float* w, const float* b, int n, TO* y,
+                     int64_t ldc, int relu, cudaStream_t s);
+
+template <typename TO>
+static int launch_any(int impl, const float* x, int64_t m, int k, int64_t lda, const float* w, const float* b, int n, TO* y,
+                      int64_t ldc, int relu, cudaStream_t s) {
+  return impl == 1 ? launch_linear_tc<TO>(x, m, k, lda, w, b, n, y, ldc, relu, s)
+                   : launch_linear<TO>(x, m, k, lda, w, b, n, y, ldc, relu, s);
+}
+
 }  // namespace sixdgs
 
 using namespace sixdgs;
@@ -111,12 +126,13 @@ extern "C" int sixdgs_ray_features(const float* ori, const float* dir, const flo
                                    const float* w1p, const float* b1, const float* w2, const float* b2,
                                    const float* w3p, const float* b3, const float* w4, const float* b4,
                                    const float* wk, const float* bk, void* k_out, int k_dtype, float* feat_out,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+                                   int impl, void* workspace, size_t workspace_bytes, void* stream) {
   SIXDGS_REQUIRE(ori && dir && rgb && w1p && b1 && w2 && b2 && w3p && b3 && w4 && b4, "null pointer");
   SIXDGS_REQUIRE(k_out || feat_out, "no output requested");
   SIXDGS_REQUIRE(!k_out || k_dtype == SIXDGS_F32 || k_dtype == SIXDGS_BF16, "unsupported k_dtype");
   SIXDGS_REQUIRE(!k_out || !wk || bk, "wk without bk");
   SIXDGS_REQUIRE(n >= 0, "negative size");
+  SIXDGS_REQUIRE(impl == 0 || impl == 1, "impl must be 0 (fp32 SIMT) or 1 (TF32 tcgen05)");
   if (n == 0) return SIXDGS_OK;
   if (workspace == nullptr || workspace_bytes < sixdgs_ray_features_workspace(n)) {
     set_error("ray_features: workspace too small (%zu < %zu)", workspace_bytes, sixdgs_ray_features_workspace(n));
@@ -133,30 +149,30 @@ extern "C" int sixdgs_ray_features(const float* ori, const float* dir, const flo
     int rc = check_launch("pe");
     if (rc) return rc;
     // mlp.0: x(144) -> H(512), relu ; mlp.2: H -> X[:, :512], relu
-    if ((rc = launch_linear<float>(X + 512, c, 144, kXW, w1p, b1, 512, H, 512, 1, s))) return rc;
-    if ((rc = launch_linear<float>(H, c, 512, 512, w2, b2, 512, X, kXW, 1, s))) return rc;
+    if ((rc = launch_any<float>(impl, X + 512, c, kInPad, kXW, w1p, b1, 512, H, 512, 1, s))) return rc;
+    if ((rc = launch_any<float>(impl, H, c, 512, 512, w2, b2, 512, X, kXW, 1, s))) return rc;
     // mlp2.0: [h, x](656) -> H(512), relu ; mlp2.2: H -> feature(384)
-    if ((rc = launch_linear<float>(X, c, kXW, kXW, w3p, b3, 512, H, 512, 1, s))) return rc;
+    if ((rc = launch_any<float>(impl, X, c, kXW, kXW, w3p, b3, 512, H, 512, 1, s))) return rc;
     const bool project = (k_out != nullptr) && (wk != nullptr);
     float* fdst = feat_out ? feat_out + r0 * kFeat : F;
     if (!project && k_out && !feat_out) {
       // no projection: the feature itself is the requested output
       if (k_dtype == SIXDGS_F32)
-        rc = launch_linear<float>(H, c, 512, 512, w4, b4, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s);
+        rc = launch_any<float>(impl, H, c, 512, 512, w4, b4, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s);
       else
-        rc = launch_linear<__nv_bfloat16>(H, c, 512, 512, w4, b4, kFeat, (__nv_bfloat16*)k_out + r0 * kFeat,
-                                          kFeat, 0, s);
+        rc = launch_any<__nv_bfloat16>(impl, H, c, 512, 512, w4, b4, kFeat, (__nv_bfloat16*)k_out + r0 * kFeat,
+                                       kFeat, 0, s);
       if (rc) return rc;
       continue;
     }
-    if ((rc = launch_linear<float>(H, c, 512, 512, w4, b4, kFeat, fdst, kFeat, 0, s))) return rc;
+    if ((rc = launch_any<float>(impl, H, c, 512, 512, w4, b4, kFeat, fdst, kFeat, 0, s))) return rc;
     if (k_out) {
       if (project) {
         if (k_dtype == SIXDGS_F32)
-          rc = launch_linear<float>(fdst, c, kFeat, kFeat, wk, bk, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s);
+          rc = launch_any<float>(impl, fdst, c, kFeat, kFeat, wk, bk, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s);
         else
-          rc = launch_linear<__nv_bfloat16>(fdst, c, kFeat, kFeat, wk, bk, kFeat,
-                                            (__nv_bfloat16*)k_out + r0 * kFeat, kFeat, 0, s);
+          rc = launch_any<__nv_bfloat16>(impl, fdst, c, kFeat, kFeat, wk, bk, kFeat,
+                                         (__nv_bfloat16*)k_out + r0 * kFeat, kFeat, 0, s);
       } else {
         // identity "projection" of the stored feature into k_out (dtype conversion only)
         set_error("ray_features: k_out without wk requires feat_out == NULL");

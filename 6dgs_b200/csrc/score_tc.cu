@@ -24,9 +24,7 @@
 //     4..11 = epilogue (two warps per TMEM lane quadrant, 128 columns each).
 // log2(e)/sqrt(384) is folded into Q when it is converted to bf16, so the epilogue is FADD + MUFU.EX2
 // + FADD per logit.
-#include <cuda.h>
-#include <cudaTypedefs.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sixdgs {
 
@@ -56,7 +54,6 @@ struct __align__(1024) TcSmem {
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -64,22 +61,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "LAB_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE_%=;\n\t"
-      "bra LAB_WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
@@ -89,10 +70,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit: address of the pair leader's barrier
 
 // 2-CTA TMA load: both CTAs issue it for their own shared memory; the transaction bytes are
@@ -105,19 +82,8 @@ __device__ __forceinline__ void tma_load_2sm(void* smem_dst, const CUtensorMap* 
       : "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1, LBO 16 B (unused),
-// SBO = 1024 B between 8-row groups, layout type 2).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 // kind::f16, bf16 x bf16 -> fp32, A and B K-major, M = 256 (cta_group::2), N = 256
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+constexpr uint32_t kIdesc = umma_idesc(1, 256, 256);
 
 __device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
@@ -134,27 +100,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
           smem_u32(bar)),
       "h"((uint16_t)3)
       : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
-        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
-        "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
-        "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
-      : "r"(taddr));
-}
-// The destination registers of tcgen05.ld are written asynchronously; tying all 32 of them to the wait
-// as in/out operands stops the compiler from scheduling any use of them above the wait.
-__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
-                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
-                 "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
-                 "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
-               :
-               : "memory");
 }
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -395,31 +340,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------ host side
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  return fn;
-}
-
-// 2-D bf16 tensor [rows, 384] row-major; box = 64 columns (128 B) x 128 rows; SWIZZLE_128B; OOB rows read as 0
 static int make_map(CUtensorMap* map, const void* base, uint64_t rows) {
-  auto enc = get_encode();
-  if (!enc) { set_error("score_tc: cuTensorMapEncodeTiled unavailable"); return SIXDGS_EUNSUPPORTED; }
-  const cuuint64_t dims[2] = {(cuuint64_t)kFeat, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)kFeat * sizeof(__nv_bfloat16)};
-  const cuuint32_t box[2] = {64, 128};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("score_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return SIXDGS_ECUDA; }
-  return SIXDGS_OK;
+  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, kFeat, (uint64_t)kFeat * 2, "score_tc");
 }
 
 size_t score_tc_workspace() { return (size_t)kMaxTokens * kFeat * sizeof(__nv_bfloat16) + 1024; }

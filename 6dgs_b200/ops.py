@@ -75,14 +75,14 @@ def raygen(xyz, scaling_raw, rotation_raw, features, sh_degree: int, sel: torch.
 
 
 def pack_ray_mlp_weights(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
-    """Zero-pad the reference state-dict matrices so every reduction dim is a multiple of 16
+    """Zero-pad the reference state-dict matrices so every reduction dim is a multiple of 32
     (layout documented in include/sixdgs.h)."""
     def g(k):
         return sd[k].detach().to(device=device, dtype=torch.float32)
 
-    w1 = torch.zeros(512, 144, device=device)
+    w1 = torch.zeros(512, 160, device=device)
     w1[:, :141] = g("ray_preprocessor.mlp.0.weight")
-    w3 = torch.zeros(512, 656, device=device)
+    w3 = torch.zeros(512, 672, device=device)
     w3[:, :653] = g("ray_preprocessor.mlp2.0.weight")
     wq = torch.zeros(FEAT, 400, device=device)
     wq[:, :398] = g("attention.q_proj.weight")
@@ -96,8 +96,12 @@ def pack_ray_mlp_weights(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch
     }
 
 
+FEATURES_SIMT = 0  # fp32 FMA GEMMs (exact)
+FEATURES_TC = 1    # TF32 tcgen05 GEMMs
+
+
 def ray_features(ori, dirs, rgb, pw: Dict[str, torch.Tensor], k_dtype: Optional[int] = F32, want_features: bool = False,
-                 project: bool = True):
+                 project: bool = True, impl: int = FEATURES_SIMT):
     """-> (K cache [n,384] in k_dtype or None, features [n,384] fp32 or None)."""
     ori, dirs, rgb = f32c(ori), f32c(dirs), f32c(rgb)
     n = ori.shape[0]
@@ -111,7 +115,8 @@ def ray_features(ori, dirs, rgb, pw: Dict[str, torch.Tensor], k_dtype: Optional[
     call("sixdgs_ray_features", dptr(ori), dptr(dirs), dptr(rgb), n, dptr(pw["w1p"]), dptr(pw["b1"]), dptr(pw["w2"]),
          dptr(pw["b2"]), dptr(pw["w3p"]), dptr(pw["b3"]), dptr(pw["w4"]), dptr(pw["b4"]),
          dptr(pw["wk"]) if project else None, dptr(pw["bk"]) if project else None,
-         dptr(k_out, None), k_dtype if k_dtype is not None else F32, dptr(feat), dptr(ws, torch.uint8), wsz, stream_ptr())
+         dptr(k_out, None), k_dtype if k_dtype is not None else F32, dptr(feat), impl, dptr(ws, torch.uint8), wsz,
+         stream_ptr())
     return k_out, feat
 
 

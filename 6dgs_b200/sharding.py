@@ -56,6 +56,13 @@ class CudaBackend:
 
 
 class ShardedPoseEstimator:
+    """One rank's view of a (possibly sharded) scene: its rays, its key-cache slice and the query pipeline.
+
+    ``query`` launches eagerly.  ``enable_cuda_graphs`` captures the pipeline with static buffers: a single
+    graph on one GPU; on several GPUs three graph segments with the two NCCL all-gathers issued eagerly
+    between them (a collective inside a captured graph ties the graph to NCCL's internal state and proved
+    fragile; two eager launches per query cost ~10 us)."""
+
     def __init__(self, idm, rays_ori: torch.Tensor, rays_dir: torch.Tensor, cache, rank: int = 0, world: int = 1,
                  backend=None, group=None):
         self.backend = backend or CudaBackend(idm)
@@ -67,40 +74,127 @@ class ShardedPoseEstimator:
         # q_proj 1, (qprep + pass) x2 on the tensor-core path, merge 1, top-k 11 (+11 global), pose tail 1
         tc = 2 if getattr(self.backend, "impl", 0) == ops.SCORE_TC else 0
         self.launches_per_query = 1 + 2 + tc + 1 + 11 + 1 + (11 if world > 1 else 0)
+        self._g = None  # captured graphs + static buffers
 
-    def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
+    # ------------------------------------------------------------------ collectives
+    def _all_gather(self, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         import torch.distributed as dist
 
         t = t.contiguous()
         if dist.get_backend(self.group) == "nccl":  # one collective kernel, no per-rank copies
-            out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            if out is None:
+                out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
             dist.all_gather_into_tensor(out, t, group=self.group)
             return out
         outs = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(outs, t, group=self.group)
-        return torch.cat(outs, 0)
+        res = torch.cat(outs, 0)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
-    @torch.no_grad()
-    def query(self, img: torch.Tensor, mask: torch.Tensor, k: int = 100):
-        """-> (c2w[4,4], aux[8]); identical on every rank."""
+    # ------------------------------------------------------------------ pipeline stages (no collectives inside)
+    def _stage1(self, img, mask):
+        """image -> tokens -> q, camera up, and this shard's partial softmax rows"""
         b = self.backend
         tok_pe, grid, valid = b.tokens(img, mask)
-        n_img = tok_pe.shape[0]
         q = b.project(tok_pe)
         pm, pz = b.pass1(self.cache.keys, q)
-        if self.world > 1:
-            pm, pz = self._all_gather(pm), self._all_gather(pz)
-        m, z = b.merge(pm, pz, n_img, valid)
-        scores = b.pass2(self.cache.keys, q, m, z, self.cache.scores)
+        return {"q": q, "valid": valid, "up": b.camera_up(grid), "pm": pm, "pz": pz, "n_img": tok_pe.shape[0]}
+
+    def _stage2(self, pm, pz, st, k):
+        """merged statistics -> scores -> local top-k (+ packed candidates when sharded)"""
+        b = self.backend
+        m, z = b.merge(pm, pz, st["n_img"], st["valid"])
+        scores = b.pass2(self.cache.keys, st["q"], m, z, self.cache.scores)
         k_local = min(k, self.cache.n_rays)
         vals, idx = b.topk(scores, k_local)
-        up = b.camera_up(grid)
         if self.world == 1:
-            return b.pose_tail(self.ori, self.dirs, idx, vals, up)
+            return vals, idx, None
         cand = torch.full((k, 7), float("-inf"), dtype=torch.float32, device=scores.device)
         cand[:k_local, 0] = vals
         cand[:k_local, 1:4] = self.ori[idx]
         cand[:k_local, 4:7] = self.dirs[idx]
-        allc = self._all_gather(cand)
+        return vals, idx, cand
+
+    def _stage3(self, allc, up, k):
+        b = self.backend
         gvals, gidx = b.topk(allc[:, 0].contiguous(), k)
         return b.pose_tail(allc[:, 1:4].contiguous(), allc[:, 4:7].contiguous(), gidx, gvals, up)
+
+    def _query_eager(self, img, mask, k):
+        st = self._stage1(img, mask)
+        pm, pz = st["pm"], st["pz"]
+        if self.world > 1:
+            pm, pz = self._all_gather(pm), self._all_gather(pz)
+        vals, idx, cand = self._stage2(pm, pz, st, k)
+        if self.world == 1:
+            return self.backend.pose_tail(self.ori, self.dirs, idx, vals, st["up"])
+        return self._stage3(self._all_gather(cand), st["up"], k)
+
+    # ------------------------------------------------------------------ CUDA graphs
+    def enable_cuda_graphs(self, img: torch.Tensor, mask: torch.Tensor, k: int = 100) -> bool:
+        """Capture the query for images of this shape.  Returns False (and stays eager) if capture fails."""
+        cur = torch.cuda.current_stream()
+        g = {"img": img.clone(), "mask": mask.clone(), "k": k}
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._query_eager(g["img"], g["mask"], k)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            if self.world == 1:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    g["out"] = self._query_eager(g["img"], g["mask"], k)
+                g["graphs"] = [g1]
+            else:
+                g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    g["st"] = self._stage1(g["img"], g["mask"])
+                g["pm_all"] = self._all_gather(g["st"]["pm"])
+                g["pz_all"] = self._all_gather(g["st"]["pz"])
+                with torch.cuda.graph(g2):
+                    _, _, g["cand"] = self._stage2(g["pm_all"], g["pz_all"], g["st"], k)
+                g["allc"] = self._all_gather(g["cand"])
+                with torch.cuda.graph(g3):
+                    g["out"] = self._stage3(g["allc"], g["st"]["up"], k)
+                g["graphs"] = [g1, g2, g3]
+            torch.cuda.synchronize()
+            self._g = g
+            return True
+        except Exception as e:  # noqa: BLE001
+            import sys
+            print(f"[sixdgs] CUDA graph capture unavailable ({type(e).__name__}: {e}); staying eager", file=sys.stderr)
+            self._g = None
+            torch.cuda.synchronize()
+            return False
+
+    def _query_graphs(self, img, mask):
+        g = self._g
+        if img.data_ptr() != g["img"].data_ptr():
+            g["img"].copy_(img)
+        if mask.data_ptr() != g["mask"].data_ptr():
+            g["mask"].copy_(mask)
+        if self.world == 1:
+            g["graphs"][0].replay()
+        else:
+            g["graphs"][0].replay()
+            self._all_gather(g["st"]["pm"], g["pm_all"])
+            self._all_gather(g["st"]["pz"], g["pz_all"])
+            g["graphs"][1].replay()
+            self._all_gather(g["cand"], g["allc"])
+            g["graphs"][2].replay()
+        return g["out"]
+
+    @torch.no_grad()
+    def query(self, img: torch.Tensor, mask: torch.Tensor, k: int = 100):
+        """-> (c2w[4,4], aux[8]); identical on every rank.  With graphs enabled the returned tensors are the
+        graph's static outputs (overwritten by the next query)."""
+        g = self._g
+        if g is not None and g["k"] == k and img.shape == g["img"].shape and mask.shape == g["mask"].shape:
+            return self._query_graphs(img, mask)
+        return self._query_eager(img, mask, k)

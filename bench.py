@@ -275,34 +275,19 @@ def main():
     for _ in range(max(args.warmup, 3)):
         c2w, aux = query()
     torch.cuda.synchronize()
-    graph = None
+    graph = False
     if not args.no_graph:
-        try:
-            g = torch.cuda.CUDAGraph()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    query()
-            torch.cuda.current_stream().wait_stream(s)
-            with torch.cuda.graph(g):
-                g_out = query()
-            g.replay()
+        graph = est.enable_cuda_graphs(img_dev, mask_dev)
+        if graph:
+            g_out = est.query(img_dev, mask_dev)
             torch.cuda.synchronize()
-            if torch.allclose(g_out[0], c2w, atol=1e-5, equal_nan=True):
-                graph = g
-            else:
+            if not torch.allclose(g_out[0], c2w, atol=1e-5, equal_nan=True):
                 print("[bench] CUDA graph replay does not reproduce the eager pose; timing eager launches", file=sys.stderr)
-        except Exception as e:  # noqa: BLE001
-            print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
+                est._g = None
+                graph = False
 
     def step():
-        if graph is not None:
-            graph.replay()
-        else:
-            query()
+        query()
 
     def barrier():
         if world > 1:
@@ -334,11 +319,13 @@ def main():
     # ---------------- e2e: host image -> pose on host, through the public API ----------------
     pose_host = torch.empty(4, 4).pin_memory()
 
+    img_e2e = torch.empty_like(img_dev)
+
     def e2e_step():
         d = img_host.to(dev, non_blocking=True)
-        img = d.float() / 255.0
-        m = torch.ones_like(img[..., 0], dtype=torch.bool)
-        c, _ = est.query(img, m)
+        torch.div(d, 255.0, out=img_e2e)  # uint8 -> [0,1] float (test.py:69-73)
+        m = torch.ones_like(img_e2e[..., 0], dtype=torch.bool)
+        c, _ = est.query(img_e2e, m)
         pose_host.copy_(c, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -408,7 +395,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if "bf16" in args.score_impl else "f32",
                 "data": "synthetic", "config": workload_config(args, n_total, n_local), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": est.launches_per_query * args.steps, "cuda_graph": graph is not None,
+                "gpu_launches": est.launches_per_query * args.steps, "cuda_graph": bool(graph),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "prepare": {"scene_to_gpu_s": t1 - t0, "raygen_s": t2 - t1, "key_cache_s": t3 - t2,
                             "rays_per_s_raygen": n_local / max(t2 - t1, 1e-9)},

@@ -85,20 +85,21 @@ int sixdgs_exclusive_scan(const int32_t* in, int64_t n, int64_t* out, void* stre
 
 /* ---- a10 (+ k_proj of a11): ray features -> key cache -------- ray_preprocessor.py:3-46,
  *                                                               our_multihead_attention.py:75
- * Packed weights (built once by the host, zero padded so every K dim is a multiple of 16):
- *   w1p[512,144]  = mlp.0.weight  (141 -> 144)        b1[512]
+ * Packed weights (built once by the host, zero padded so every K dim is a multiple of 32):
+ *   w1p[512,160]  = mlp.0.weight  (141 -> 160)        b1[512]
  *   w2 [512,512]  = mlp.2.weight                      b2[512]
- *   w3p[512,656]  = mlp2.0.weight ([h512 | x141] -> 656) b3[512]
+ *   w3p[512,672]  = mlp2.0.weight ([h512 | x141] -> 672) b3[512]
  *   w4 [384,512]  = mlp2.2.weight                     b4[384]
  *   wk [384,384]  = attention.k_proj.weight (nullable: skip projection, emit features) bk[384]
  * k_out[n,384] in k_dtype (SIXDGS_F32 | SIXDGS_BF16); feat_out (nullable) = pre-projection features.
+ * impl: 0 = fp32 FMA GEMMs (exact path), 1 = TF32 tcgen05 GEMMs (TMA + TMEM; throughput path).
  * workspace >= sixdgs_ray_features_workspace(n) bytes. */
 size_t sixdgs_ray_features_workspace(int64_t n);
 int sixdgs_ray_features(const float* ori, const float* dir, const float* rgb, int64_t n,
                         const float* w1p, const float* b1, const float* w2, const float* b2,
                         const float* w3p, const float* b3, const float* w4, const float* b4,
                         const float* wk, const float* bk, void* k_out, int k_dtype, float* feat_out,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        int impl, void* workspace, size_t workspace_bytes, void* stream);
 
 /* generic y[m,n] = act(x[m,k] w[n,k]^T + b[n]); k % 16 == 0, lda/ldc in elements (used for q_proj,
  * our_multihead_attention.py:74, with img features padded 398 -> 400). */

@@ -364,3 +364,30 @@ def test_fused_query_dense_tokens_equals_compacted(sx, module_fp32):
         est = sx.ShardedPoseEstimator(module_fp32, ori, dirs, module_fp32._cache_for(ori, dirs, rgb))
         c2w, _ = est.query(img, mask)
         torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_ray_features_tf32_tensor_core_vs_fp32(sx, module_fp32):
+    """TF32 tcgen05 build of the key cache against the exact fp32 build and the reference fixture.
+    TF32 keeps 10 mantissa bits per operand: 2e-3 of the key magnitude after five layers is the budget
+    (the bf16 rounding of the stored keys is 4e-3)."""
+    g = load_golden("id_module.npz")
+    r = load_golden("rays_small.npz")
+    gen = torch.Generator().manual_seed(3)
+    for n in (1, 130, 5513, 200_000):
+        if n <= 5513:
+            ori, dirs, rgb = cu(r["ori"][:n]), cu(r["dirs"][:n]), cu(r["rgb"][:n])
+        else:  # several 131072-ray chunks + a ragged tail
+            ori = (torch.randn(n, 3, generator=gen) * 3).to(DEV)
+            dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1).to(DEV)
+            rgb = torch.rand(n, 3, generator=gen).to(DEV)
+        pw = module_fp32.packed_weights()
+        k_ref, f_ref = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.F32, want_features=True, impl=sx.ops.FEATURES_SIMT)
+        k_tc, f_tc = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.F32, want_features=True, impl=sx.ops.FEATURES_TC)
+        scale = k_ref.abs().max().item()
+        assert (k_tc - k_ref).abs().max().item() <= 2e-3 * scale, (n, (k_tc - k_ref).abs().max().item(), scale)
+        assert (f_tc - f_ref).abs().max().item() <= 2e-3 * f_ref.abs().max().item()
+        k_bf, _ = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.BF16, impl=sx.ops.FEATURES_TC)
+        assert k_bf.dtype == torch.bfloat16 and (k_bf.float() - k_ref).abs().max().item() <= 6e-3 * scale
+        if n == 5513:
+            sel = g["fea_sel"].to(DEV)
+            torch.testing.assert_close(k_tc[sel].cpu(), g["k_sel"], rtol=0, atol=2e-3 * scale)
