@@ -23,8 +23,14 @@ constexpr int kIn = 141;
 
 // x = [ori3, dir3, rgb3, sin(ori*2^f) (coordinate-major, f=0..7), cos(..), sin(dir*2^f), cos(..),
 //      sin(rgb*2^f) f=0..5, cos(..)]                                  ray_preprocessor.py:3-9,36-44
+__device__ __forceinline__ float rna_tf32(float v) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+  return __uint_as_float(t);
+}
+
 __global__ void pe_kernel(const float* __restrict__ ori, const float* __restrict__ dir,
-                          const float* __restrict__ rgb, int64_t n, float* __restrict__ X) {
+                          const float* __restrict__ rgb, int64_t n, float* __restrict__ X, int round_tf32) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   float* x = X + r * kXW + 512;
@@ -47,6 +53,9 @@ __global__ void pe_kernel(const float* __restrict__ ori, const float* __restrict
   }
 #pragma unroll
   for (int i = kIn; i < kInPad; ++i) x[i] = 0.f;
+  if (round_tf32) {  // tensor-core path: make the TF32 truncation of the MMA exact (see features_tc.cu)
+    for (int i = 0; i < kIn; ++i) x[i] = rna_tf32(x[i]);
+  }
 }
 
 template <typename TO>
@@ -95,12 +104,13 @@ static int launch_linear(const float* x, int64_t m, int k, int64_t lda, const fl
 // tensor-core (TF32 tcgen05) GEMM, features_tc.cu
 template <typename TO>
 int launch_linear_tc(const float* x, int64_t m, int k, int64_t lda, const float* w, const float* b, int n, TO* y,
-                     int64_t ldc, int relu, cudaStream_t s);
+                     int64_t ldc, int relu, int round_tf32, cudaStream_t s);
 
+// `feeds_gemm`: the output is the A operand of another tensor-core layer -> round it to TF32 on store
 template <typename TO>
 static int launch_any(int impl, const float* x, int64_t m, int k, int64_t lda, const float* w, const float* b, int n, TO* y,
-                      int64_t ldc, int relu, cudaStream_t s) {
-  return impl == 1 ? launch_linear_tc<TO>(x, m, k, lda, w, b, n, y, ldc, relu, s)
+                      int64_t ldc, int relu, cudaStream_t s, int feeds_gemm = 1) {
+  return impl == 1 ? launch_linear_tc<TO>(x, m, k, lda, w, b, n, y, ldc, relu, feeds_gemm, s)
                    : launch_linear<TO>(x, m, k, lda, w, b, n, y, ldc, relu, s);
 }
 
@@ -145,7 +155,7 @@ extern "C" int sixdgs_ray_features(const float* ori, const float* dir, const flo
   float* F = H + cap * 512;
   for (int64_t r0 = 0; r0 < n; r0 += cap) {
     const int64_t c = (n - r0) < cap ? (n - r0) : cap;
-    pe_kernel<<<(unsigned)((c + 127) / 128), 128, 0, s>>>(ori + r0 * 3, dir + r0 * 3, rgb + r0 * 3, c, X);
+    pe_kernel<<<(unsigned)((c + 127) / 128), 128, 0, s>>>(ori + r0 * 3, dir + r0 * 3, rgb + r0 * 3, c, X, impl == 1);
     int rc = check_launch("pe");
     if (rc) return rc;
     // mlp.0: x(144) -> H(512), relu ; mlp.2: H -> X[:, :512], relu
@@ -158,21 +168,22 @@ extern "C" int sixdgs_ray_features(const float* ori, const float* dir, const flo
     if (!project && k_out && !feat_out) {
       // no projection: the feature itself is the requested output
       if (k_dtype == SIXDGS_F32)
-        rc = launch_any<float>(impl, H, c, 512, 512, w4, b4, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s);
+        rc = launch_any<float>(impl, H, c, 512, 512, w4, b4, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s, 0);
       else
         rc = launch_any<__nv_bfloat16>(impl, H, c, 512, 512, w4, b4, kFeat, (__nv_bfloat16*)k_out + r0 * kFeat,
-                                       kFeat, 0, s);
+                                       kFeat, 0, s, 0);
       if (rc) return rc;
       continue;
     }
-    if ((rc = launch_any<float>(impl, H, c, 512, 512, w4, b4, kFeat, fdst, kFeat, 0, s))) return rc;
+    // the feature feeds k_proj when a projection follows; if it is also returned to the caller keep it unrounded
+    if ((rc = launch_any<float>(impl, H, c, 512, 512, w4, b4, kFeat, fdst, kFeat, 0, s, (project && !feat_out) ? 1 : 0))) return rc;
     if (k_out) {
       if (project) {
         if (k_dtype == SIXDGS_F32)
-          rc = launch_any<float>(impl, fdst, c, kFeat, kFeat, wk, bk, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s);
+          rc = launch_any<float>(impl, fdst, c, kFeat, kFeat, wk, bk, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s, 0);
         else
           rc = launch_any<__nv_bfloat16>(impl, fdst, c, kFeat, kFeat, wk, bk, kFeat,
-                                         (__nv_bfloat16*)k_out + r0 * kFeat, kFeat, 0, s);
+                                         (__nv_bfloat16*)k_out + r0 * kFeat, kFeat, 0, s, 0);
       } else {
         // identity "projection" of the stored feature into k_out (dtype conversion only)
         set_error("ray_features: k_out without wk requires feat_out == NULL");

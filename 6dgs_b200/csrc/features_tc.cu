@@ -11,8 +11,12 @@
 //   warps 4..7  epilogue: tcgen05.ld -> +bias -> ReLU -> fp32 / bf16 stores (one output row per thread,
 //               full 128-byte lines), overlapped with the next tile's MMAs.
 // Tiles are ordered n-fastest so the x tile is re-read from L2, not HBM, by the N/128 CTAs that share it.
-// Used for the bf16 (throughput) key cache: TF32 rounds operands to 10 mantissa bits (2^-11), below the
-// 2^-9 rounding of the bf16 keys themselves; the exact (fp32-key) mode keeps the fp32 SIMT GEMMs.
+// Used for the bf16 (throughput) key cache; the exact (fp32-key) mode keeps the fp32 SIMT GEMMs.
+// kind::tf32 reads fp32 words and TRUNCATES them to 10 mantissa bits, which biases every product towards
+// zero (measured: 3e-3 relative on the keys after five layers).  Operands are therefore pre-rounded to
+// TF32 with round-to-nearest where they are produced: the weights once at packing time, the activations
+// in the epilogue that writes them (`round_tf32`), the MLP input in the PE kernel.  The truncation is
+// then exact and the remaining error is unbiased (2^-12 per operand).
 #include "tc_common.cuh"
 
 namespace sixdgs {
@@ -63,7 +67,7 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const fl
 template <typename TO>
 __global__ void __launch_bounds__(kLtThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, int64_t m, int k,
-                 int n, const float* __restrict__ bias, TO* __restrict__ y, int64_t ldc, int relu) {
+                 int n, const float* __restrict__ bias, TO* __restrict__ y, int64_t ldc, int relu, int round_tf32) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   LtSmem& sm = *reinterpret_cast<LtSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -163,6 +167,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
               for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
             }
+            if (round_tf32) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                uint32_t t;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(o[e]));
+                o[e] = __uint_as_float(t);
+              }
+            }
             store8<TO>(y + row * ldc + col0 + c * 32 + j, o);
           }
         }
@@ -184,7 +196,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // y = act(x w^T + b) on the tensor cores.  x [m, k] fp32 with row stride lda (elements), w [n, k] fp32 dense.
 template <typename TO>
 int launch_linear_tc(const float* x, int64_t m, int k, int64_t lda, const float* w, const float* b, int n, TO* y,
-                     int64_t ldc, int relu, cudaStream_t s) {
+                     int64_t ldc, int relu, int round_tf32, cudaStream_t s) {
   if (k % kLtBK != 0 || n % kLtBN != 0 || (lda % 4) != 0 || (ldc % 8) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) ||
       (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) {
     set_error("linear_tc: k %% 32, n %% 128, lda %% 4, ldc %% 8 and 16-byte alignment are required");
@@ -201,13 +213,13 @@ int launch_linear_tc(const float* x, int64_t m, int k, int64_t lda, const float*
   if (e != cudaSuccess) { set_error("linear_tc attr: %s", cudaGetErrorString(e)); return SIXDGS_ECUDA; }
   const int64_t tiles = ((m + kLtBM - 1) / kLtBM) * (n / kLtBN);
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  linear_tc_kernel<TO><<<grid, kLtThreads, smem, s>>>(mx, mw, m, k, n, b, y, ldc, relu);
+  linear_tc_kernel<TO><<<grid, kLtThreads, smem, s>>>(mx, mw, m, k, n, b, y, ldc, relu, round_tf32);
   return check_launch("linear_tc");
 }
 
 template int launch_linear_tc<float>(const float*, int64_t, int, int64_t, const float*, const float*, int, float*, int64_t,
-                                     int, cudaStream_t);
+                                     int, int, cudaStream_t);
 template int launch_linear_tc<__nv_bfloat16>(const float*, int64_t, int, int64_t, const float*, const float*, int,
-                                             __nv_bfloat16*, int64_t, int, cudaStream_t);
+                                             __nv_bfloat16*, int64_t, int, int, cudaStream_t);
 
 }  // namespace sixdgs

@@ -86,7 +86,14 @@ def pack_ray_mlp_weights(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch
     w3[:, :653] = g("ray_preprocessor.mlp2.0.weight")
     wq = torch.zeros(FEAT, 400, device=device)
     wq[:, :398] = g("attention.q_proj.weight")
-    return {
+
+    def tf32(t):
+        """round-to-nearest onto the TF32 grid (10 mantissa bits): the tensor-core GEMMs truncate fp32 operands,
+        pre-rounding makes that truncation exact (features_tc.cu)"""
+        i = t.contiguous().view(torch.int32)
+        return ((i + 0x1000) & -8192).view(torch.float32)
+
+    pw = {
         "w1p": w1.contiguous(), "b1": g("ray_preprocessor.mlp.0.bias").contiguous(),
         "w2": g("ray_preprocessor.mlp.2.weight").contiguous(), "b2": g("ray_preprocessor.mlp.2.bias").contiguous(),
         "w3p": w3.contiguous(), "b3": g("ray_preprocessor.mlp2.0.bias").contiguous(),
@@ -94,6 +101,9 @@ def pack_ray_mlp_weights(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch
         "wk": g("attention.k_proj.weight").contiguous(), "bk": g("attention.k_proj.bias").contiguous(),
         "wqp": wq.contiguous(), "bq": g("attention.q_proj.bias").contiguous(),
     }
+    for k in ("w1p", "w2", "w3p", "w4", "wk"):
+        pw[k + "_tf32"] = tf32(pw[k])
+    return pw
 
 
 FEATURES_SIMT = 0  # fp32 FMA GEMMs (exact)
@@ -112,9 +122,10 @@ def ray_features(ori, dirs, rgb, pw: Dict[str, torch.Tensor], k_dtype: Optional[
     feat = torch.empty(n, FEAT, dtype=torch.float32, device=dev) if want_features else None
     wsz = int(_lib.load().sixdgs_ray_features_workspace(n))
     ws = torch.empty(wsz, dtype=torch.uint8, device=dev)
-    call("sixdgs_ray_features", dptr(ori), dptr(dirs), dptr(rgb), n, dptr(pw["w1p"]), dptr(pw["b1"]), dptr(pw["w2"]),
-         dptr(pw["b2"]), dptr(pw["w3p"]), dptr(pw["b3"]), dptr(pw["w4"]), dptr(pw["b4"]),
-         dptr(pw["wk"]) if project else None, dptr(pw["bk"]) if project else None,
+    sfx = "_tf32" if impl == FEATURES_TC else ""
+    call("sixdgs_ray_features", dptr(ori), dptr(dirs), dptr(rgb), n, dptr(pw["w1p" + sfx]), dptr(pw["b1"]),
+         dptr(pw["w2" + sfx]), dptr(pw["b2"]), dptr(pw["w3p" + sfx]), dptr(pw["b3"]), dptr(pw["w4" + sfx]), dptr(pw["b4"]),
+         dptr(pw["wk" + sfx]) if project else None, dptr(pw["bk"]) if project else None,
          dptr(k_out, None), k_dtype if k_dtype is not None else F32, dptr(feat), impl, dptr(ws, torch.uint8), wsz,
          stream_ptr())
     return k_out, feat

@@ -48,6 +48,9 @@ def generate_all_possible_rays(model, num_viewdirs_per_chunk: int = 10240, sampl
     sel = valid_ids[ellipsoid_idx].contiguous()
     centers = xyz[sel].contiguous()
     m = sel.shape[0]
+    if m == 0:  # every ellipsoid degraded (or an empty scene): no rays
+        e = torch.empty(0, 3, dtype=torch.float32, device=dev)
+        return (e, e.clone(), e.clone(), sel) if return_ids else (e, e.clone(), e.clone())
     lo, hi = 0, m
     if shard is not None:
         rank, world = shard

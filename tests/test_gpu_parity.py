@@ -368,8 +368,8 @@ def test_fused_query_dense_tokens_equals_compacted(sx, module_fp32):
 
 def test_ray_features_tf32_tensor_core_vs_fp32(sx, module_fp32):
     """TF32 tcgen05 build of the key cache against the exact fp32 build and the reference fixture.
-    TF32 keeps 10 mantissa bits per operand: 2e-3 of the key magnitude after five layers is the budget
-    (the bf16 rounding of the stored keys is 4e-3)."""
+    Operands are pre-rounded (nearest) to TF32's 10 mantissa bits, so the error is unbiased: 1.5e-3 of the
+    key magnitude after five layers is the budget (the bf16 rounding of the stored keys alone is 2e-3)."""
     g = load_golden("id_module.npz")
     r = load_golden("rays_small.npz")
     gen = torch.Generator().manual_seed(3)
@@ -384,10 +384,61 @@ def test_ray_features_tf32_tensor_core_vs_fp32(sx, module_fp32):
         k_ref, f_ref = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.F32, want_features=True, impl=sx.ops.FEATURES_SIMT)
         k_tc, f_tc = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.F32, want_features=True, impl=sx.ops.FEATURES_TC)
         scale = k_ref.abs().max().item()
-        assert (k_tc - k_ref).abs().max().item() <= 2e-3 * scale, (n, (k_tc - k_ref).abs().max().item(), scale)
-        assert (f_tc - f_ref).abs().max().item() <= 2e-3 * f_ref.abs().max().item()
+        assert (k_tc - k_ref).abs().max().item() <= 1.5e-3 * scale, (n, (k_tc - k_ref).abs().max().item(), scale)
+        assert (f_tc - f_ref).abs().max().item() <= 1.5e-3 * f_ref.abs().max().item()
         k_bf, _ = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.BF16, impl=sx.ops.FEATURES_TC)
-        assert k_bf.dtype == torch.bfloat16 and (k_bf.float() - k_ref).abs().max().item() <= 6e-3 * scale
+        assert k_bf.dtype == torch.bfloat16 and (k_bf.float() - k_ref).abs().max().item() <= 4e-3 * scale
         if n == 5513:
             sel = g["fea_sel"].to(DEV)
             torch.testing.assert_close(k_tc[sel].cpu(), g["k_sel"], rtol=0, atol=2e-3 * scale)
+
+
+# ------------------------------------------------------------------------------------ edge cases
+def test_edge_cases_empty_and_degenerate(sx, synthetic, module_fp32):
+    z3 = torch.zeros(0, 3, device=DEV)
+    valid, rings = sx.ops.degrade_mask(z3)
+    assert valid.numel() == 0 and rings.numel() == 0
+    k, f = sx.ops.ray_features(z3, z3, z3, module_fp32.packed_weights(), k_dtype=sx._lib.F32, want_features=True)
+    assert k.shape == (0, 384) and f.shape == (0, 384)
+    assert sx.sym_eig_3x3(torch.zeros(0, 3, 3, device=DEV))[0].shape == (0, 3)
+    with pytest.raises(sx.SixdgsError):
+        sx.ops.knn_normals(torch.randn(5, 3, device=DEV), 20)  # fewer points than neighbours
+    # a scene whose ellipsoids are all needles (rings >= 50): everything is masked out, zero rays
+    sc = synthetic.synth_scene(64, seed=1)
+    sc["scaling"] = torch.log(torch.tensor([[5.0, 1e-3, 1e-3]])).repeat(64, 1)
+    scene = sx.GaussianScene.from_dict(sc, device=DEV)
+    valid, rings = sx.ops.degrade_mask(scene._scaling)
+    assert not valid.any() and (rings >= 50).all()
+    ori, dirs, rgb = sx.generate_all_possible_rays(scene, max_ellipsoids=None)
+    assert ori.shape == dirs.shape == rgb.shape == (0, 3)
+    # no rays at all: LS on an empty set is singular -> NaN vector (det(0) < 1e-7), like the reference
+    c = sx.compute_line_intersection_impl2(z3, z3)
+    assert torch.isnan(c).all()
+    # one ray, fewer rays than a tile, in both score implementations
+    for impl, dt in ((sx.ops.SCORE_SIMT, torch.float32), (sx.ops.SCORE_TC, torch.bfloat16)):
+        K = torch.randn(3, 384, device=DEV).to(dt)
+        q = torch.randn(256, 384, device=DEV)
+        pm, pz = sx.ops.score_pass1(K, q, impl)
+        m, z = sx.ops.score_merge(pm, pz, 256)
+        s, _ = sx.ops.score_pass2(K, q, m, z, impl)
+        assert abs(s.sum().item() - 256.0) < 0.05 and torch.isfinite(s).all()
+
+
+def test_heavy_tailed_scene_ray_counts_vs_oracle(sx, synthetic, oracle):
+    """load-balance stress: log-normal scales (cells per ellipsoid vary 10x); per-ellipsoid ray counts must
+    match the oracle on the same selection except where a kNN normal differs in sign."""
+    sc = synthetic.synth_scene(400, seed=21, heavy_tail=True)
+    scene = sx.GaussianScene.from_dict(sc, device=DEV)
+    valid = oracle.mask_degraded_ellipsoids(*torch.exp(sc["scaling"]).unbind(-1))
+    perm = torch.randperm(int(valid.sum()), generator=torch.Generator().manual_seed(5))
+    ori, dirs, rgb, gid = sx.generate_all_possible_rays(scene, ellipsoid_idx=perm, return_ids=True)
+    o_ori, _, o_rgb, aux = oracle.generate_rays(sc["xyz"], sc["scaling"], sc["rotation"],
+                                                torch.cat((sc["features_dc"], sc["features_rest"]), 1),
+                                                ellipsoid_idx=perm, return_aux=True)
+    cnt = torch.bincount(gid.cpu(), minlength=400)
+    cnt_ref = torch.bincount(aux["gid"], minlength=400)
+    assert (cnt == cnt_ref).float().mean().item() >= 0.97
+    assert abs(int(cnt.sum()) - int(cnt_ref.sum())) <= 0.01 * int(cnt_ref.sum())
+    if ori.shape[0] == o_ori.shape[0]:
+        frac = ((ori.cpu() - o_ori).abs().max(dim=1).values <= 1e-5 * (1 + o_ori.abs().max(dim=1).values)).float().mean().item()
+        assert frac >= 0.97
