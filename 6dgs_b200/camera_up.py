@@ -28,13 +28,17 @@ class CameraDirectionPredictor(torch.nn.Module):
         algorithms for these 384-channel 5x5 layers whose results differ from the fp32 direct sum by ~2e-4
         relative -- more than the 1e-4 pose tolerance once it reaches the rotation; a plain GEMM does not."""
         k = conv.kernel_size[0]
-        cols = torch.nn.functional.unfold(x, k)  # [1, C*k*k, L]
-        out = conv.weight.view(conv.out_channels, -1) @ cols[0] + conv.bias[:, None]
+        cols = torch.nn.functional.unfold(x, k)  # [B, C*k*k, L]
+        out = conv.weight.view(conv.out_channels, -1) @ cols + conv.bias[:, None]
         side = x.shape[-1] - k + 1
-        return out.view(1, conv.out_channels, side, side)
+        return out.view(x.shape[0], conv.out_channels, side, side)
 
-    def forward(self, image_features: torch.Tensor) -> torch.Tensor:
-        y = image_features[None]
+    def forward_batch(self, image_features: torch.Tensor) -> torch.Tensor:
+        """[B,384,16,16] -> [B,3]"""
+        y = image_features
         for conv in (self.dim_reducer1[0], self.dim_reducer1[2], self.dim_reducer1[4], self.dim_reducer2[0]):
             y = torch.relu(self._conv_gemm(y, conv))
-        return self.mlp(y.view(y.shape[0], -1))[0]
+        return self.mlp(y.reshape(y.shape[0], -1))
+
+    def forward(self, image_features: torch.Tensor) -> torch.Tensor:
+        return self.forward_batch(image_features[None])[0]

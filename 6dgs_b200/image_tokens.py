@@ -132,16 +132,23 @@ class BackboneWrapper(torch.nn.Module):
         ang = (pos[..., None] * bands).reshape(pos.shape[0], -1)
         return torch.cat([pos, torch.sin(ang), torch.cos(ang)], dim=-1).reshape(*shape, -1)
 
+    def tokens_dense_batch(self, imgs: torch.Tensor, masks: torch.Tensor):
+        """Batched, sync-free front end: imgs [B,H,W,3] in [0,1], masks [B,H,W] bool ->
+        (tokens+pe [B,16,16,398], tokens [B,16,16,384], keep [B,16,16] bool).  One backbone pass for the batch."""
+        x = self.transformations(imgs.permute(0, 3, 1, 2))
+        x = (x - self.norm_mean.view(1, 3, 1, 1)) / self.norm_std.view(1, 3, 1, 1)
+        keep = self.mask_transformations(masks[:, None] * 1.0)[:, 0] > 0.1
+        gh, gw = self.backbone_wh
+        b = imgs.shape[0]
+        tok = self.image_preprocessing_net.forward_features(x)["x_norm_patchtokens"].reshape(b, gh, gw, self.img_num_features)
+        pe = self.get_img_position_encoding((gh, gw), 3, dtype=imgs.dtype, device=imgs.device)
+        return torch.cat((tok, pe[None].expand(b, -1, -1, -1)), dim=-1), tok, keep
+
     def tokens_dense(self, img: torch.Tensor, mask: torch.Tensor):
         """All 256 grid tokens plus their validity, no host synchronisation:
-        -> (tokens+pe [256,398], tokens [16,16,384], keep [16,16] bool)."""
-        x = self.transformations(img[None].permute(0, 3, 1, 2))
-        x = (x - self.norm_mean.view(1, 3, 1, 1)) / self.norm_std.view(1, 3, 1, 1)
-        keep = self.mask_transformations(mask[None, None] * 1.0)[0, 0] > 0.1
-        gh, gw = self.backbone_wh
-        tok = self.image_preprocessing_net.forward_features(x)["x_norm_patchtokens"][0].reshape(gh, gw, self.img_num_features)
-        pe = self.get_img_position_encoding((gh, gw), 3, dtype=img.dtype, device=img.device)
-        return torch.cat((tok, pe), dim=-1), tok, keep
+        -> (tokens+pe [16,16,398], tokens [16,16,384], keep [16,16] bool)."""
+        tok_pe, tok, keep = self.tokens_dense_batch(img[None], mask[None])
+        return tok_pe[0], tok[0], keep[0]
 
     def forward(self, img: torch.Tensor, mask: torch.Tensor):
         """img [H,W,3] in [0,1], mask [H,W] bool -> (tokens+pe [n_img,398], tokens [n_img,384], grid [384,16,16]).

@@ -28,10 +28,13 @@ class CudaBackend:
         self.impl = idm._impl
         self.parts = int(_lib.load().sixdgs_score_parts(self.impl))
 
-    def tokens(self, img, mask):
-        """dense tokens: all 256 grid tokens + validity bytes, so a masked query needs no host sync"""
-        tok_pe, tok, keep = self.idm.backbone_wrapper.tokens_dense(img, mask)
-        return tok_pe.reshape(-1, tok_pe.shape[-1]).contiguous(), tok.permute(2, 0, 1), keep.reshape(-1).to(torch.uint8)
+    def tokens(self, imgs, masks):
+        """dense tokens for a batch of images [B,H,W,3]: all 256 grid tokens + validity bytes per image, so a masked
+        query needs no host sync.  -> (tok_pe [B,256,398], grid [B,384,16,16], valid [B,256] uint8)"""
+        tok_pe, tok, keep = self.idm.backbone_wrapper.tokens_dense_batch(imgs, masks)
+        b = imgs.shape[0]
+        return (tok_pe.reshape(b, -1, tok_pe.shape[-1]).contiguous(), tok.permute(0, 3, 1, 2),
+                keep.reshape(b, -1).to(torch.uint8).contiguous())
 
     def project(self, tok_pe):
         return ops.project_queries(tok_pe, self.idm.packed_weights())
@@ -49,7 +52,8 @@ class CudaBackend:
         return ops.topk(scores, k)
 
     def camera_up(self, grid):
-        return self.idm._camera_up(grid)
+        """[B,384,16,16] -> unit up vectors [B,3]"""
+        return torch.nn.functional.normalize(self.idm.camera_direction_prediction_network.forward_batch(grid), dim=-1)
 
     def pose_tail(self, ori, dirs, idx, vals, up):
         return ops.pose_tail(ori, dirs, idx, vals, up)
@@ -95,47 +99,74 @@ class ShardedPoseEstimator:
         return res
 
     # ------------------------------------------------------------------ pipeline stages (no collectives inside)
-    def _stage1(self, img, mask):
-        """image -> tokens -> q, camera up, and this shard's partial softmax rows"""
+    # Every stage works on a BATCH of B queries: the image front end (resize, backbone, q projection, up head)
+    # runs once for the batch -- it is latency-bound, so B images cost about as much as one -- while the key
+    # cache is streamed per query (two passes each).  The collectives are per batch as well.
+    def _stage1(self, imgs, masks):
+        """images -> tokens -> q, camera up, and this shard's partial softmax rows for every query of the batch"""
         b = self.backend
-        tok_pe, grid, valid = b.tokens(img, mask)
-        q = b.project(tok_pe)
-        pm, pz = b.pass1(self.cache.keys, q)
-        return {"q": q, "valid": valid, "up": b.camera_up(grid), "pm": pm, "pz": pz, "n_img": tok_pe.shape[0]}
+        tok_pe, grid, valid = b.tokens(imgs, masks)
+        nb, n_img = tok_pe.shape[0], tok_pe.shape[1]
+        q = b.project(tok_pe.reshape(nb * n_img, -1)).reshape(nb, n_img, -1)
+        parts = [b.pass1(self.cache.keys, q[i]) for i in range(nb)]
+        pm = torch.cat([p[0] for p in parts], 0)  # [B * parts, 256]
+        pz = torch.cat([p[1] for p in parts], 0)
+        return {"q": q, "valid": valid, "up": b.camera_up(grid), "pm": pm, "pz": pz, "n_img": n_img, "nb": nb,
+                "rows": parts[0][0].shape[0]}
 
     def _stage2(self, pm, pz, st, k):
-        """merged statistics -> scores -> local top-k (+ packed candidates when sharded)"""
+        """merged statistics -> scores -> local top-k per query (+ packed candidates when sharded).
+        pm/pz are [world * B * rows, 256] (rank-major); query i owns rows [r*B*rows + i*rows, +rows) of every rank r."""
         b = self.backend
-        m, z = b.merge(pm, pz, st["n_img"], st["valid"])
-        scores = b.pass2(self.cache.keys, st["q"], m, z, self.cache.scores)
+        nb, rows = st["nb"], st["rows"]
+        pm = pm.reshape(-1, nb, rows, pm.shape[-1])
+        pz = pz.reshape(-1, nb, rows, pz.shape[-1])
         k_local = min(k, self.cache.n_rays)
-        vals, idx = b.topk(scores, k_local)
-        if self.world == 1:
-            return vals, idx, None
-        cand = torch.full((k, 7), float("-inf"), dtype=torch.float32, device=scores.device)
-        cand[:k_local, 0] = vals
-        cand[:k_local, 1:4] = self.ori[idx]
-        cand[:k_local, 4:7] = self.dirs[idx]
-        return vals, idx, cand
+        vals, idxs = [], []
+        cand = None
+        if self.world > 1:
+            cand = torch.full((nb, k, 7), float("-inf"), dtype=torch.float32, device=self.ori.device)
+        for i in range(nb):
+            m, z = b.merge(pm[:, i].reshape(-1, pm.shape[-1]).contiguous(), pz[:, i].reshape(-1, pz.shape[-1]).contiguous(),
+                           st["n_img"], st["valid"][i] if st["valid"] is not None else None)
+            scores = b.pass2(self.cache.keys, st["q"][i], m, z, self.cache.scores)
+            v, ix = b.topk(scores, k_local)
+            vals.append(v)
+            idxs.append(ix)
+            if cand is not None:
+                cand[i, :k_local, 0] = v
+                cand[i, :k_local, 1:4] = self.ori[ix]
+                cand[i, :k_local, 4:7] = self.dirs[ix]
+        return vals, idxs, cand
 
-    def _stage3(self, allc, up, k):
+    def _stage3(self, allc, up, k, nb):
+        """allc [world * B, k, 7] (rank-major) -> per-query global top-k -> pose"""
         b = self.backend
-        gvals, gidx = b.topk(allc[:, 0].contiguous(), k)
-        return b.pose_tail(allc[:, 1:4].contiguous(), allc[:, 4:7].contiguous(), gidx, gvals, up)
+        allc = allc.reshape(-1, nb, allc.shape[-2], 7)
+        outs = []
+        for i in range(nb):
+            c = allc[:, i].reshape(-1, 7)
+            gvals, gidx = b.topk(c[:, 0].contiguous(), k)
+            outs.append(b.pose_tail(c[:, 1:4].contiguous(), c[:, 4:7].contiguous(), gidx, gvals, up[i]))
+        return torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
 
-    def _query_eager(self, img, mask, k):
-        st = self._stage1(img, mask)
+    def _query_eager(self, imgs, masks, k):
+        st = self._stage1(imgs, masks)
         pm, pz = st["pm"], st["pz"]
         if self.world > 1:
             pm, pz = self._all_gather(pm), self._all_gather(pz)
-        vals, idx, cand = self._stage2(pm, pz, st, k)
+        vals, idxs, cand = self._stage2(pm, pz, st, k)
         if self.world == 1:
-            return self.backend.pose_tail(self.ori, self.dirs, idx, vals, st["up"])
-        return self._stage3(self._all_gather(cand), st["up"], k)
+            outs = [self.backend.pose_tail(self.ori, self.dirs, idxs[i], vals[i], st["up"][i]) for i in range(st["nb"])]
+            return torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
+        return self._stage3(self._all_gather(cand), st["up"], k, st["nb"])
 
     # ------------------------------------------------------------------ CUDA graphs
     def enable_cuda_graphs(self, img: torch.Tensor, mask: torch.Tensor, k: int = 100) -> bool:
-        """Capture the query for images of this shape.  Returns False (and stays eager) if capture fails."""
+        """Capture the pipeline for image batches of this shape ([B,H,W,3] / [B,H,W]; a single [H,W,3] image is
+        treated as B = 1).  Returns False (and stays eager) if capture fails."""
+        if img.dim() == 3:
+            img, mask = img[None], mask[None]
         cur = torch.cuda.current_stream()
         g = {"img": img.clone(), "mask": mask.clone(), "k": k}
         try:
@@ -161,7 +192,7 @@ class ShardedPoseEstimator:
                     _, _, g["cand"] = self._stage2(g["pm_all"], g["pz_all"], g["st"], k)
                 g["allc"] = self._all_gather(g["cand"])
                 with torch.cuda.graph(g3):
-                    g["out"] = self._stage3(g["allc"], g["st"]["up"], k)
+                    g["out"] = self._stage3(g["allc"], g["st"]["up"], k, g["st"]["nb"])
                 g["graphs"] = [g1, g2, g3]
             torch.cuda.synchronize()
             self._g = g
@@ -191,10 +222,16 @@ class ShardedPoseEstimator:
         return g["out"]
 
     @torch.no_grad()
-    def query(self, img: torch.Tensor, mask: torch.Tensor, k: int = 100):
-        """-> (c2w[4,4], aux[8]); identical on every rank.  With graphs enabled the returned tensors are the
-        graph's static outputs (overwritten by the next query)."""
+    def query_batch(self, imgs: torch.Tensor, masks: torch.Tensor, k: int = 100):
+        """imgs [B,H,W,3], masks [B,H,W] -> (c2w[B,4,4], aux[B,8]); identical on every rank.  With graphs enabled
+        (for this batch shape) the returned tensors are the graph's static outputs, overwritten by the next call."""
         g = self._g
-        if g is not None and g["k"] == k and img.shape == g["img"].shape and mask.shape == g["mask"].shape:
-            return self._query_graphs(img, mask)
-        return self._query_eager(img, mask, k)
+        if g is not None and g["k"] == k and imgs.shape == g["img"].shape and masks.shape == g["mask"].shape:
+            return self._query_graphs(imgs, masks)
+        return self._query_eager(imgs, masks, k)
+
+    @torch.no_grad()
+    def query(self, img: torch.Tensor, mask: torch.Tensor, k: int = 100):
+        """single query: img [H,W,3], mask [H,W] -> (c2w[4,4], aux[8])"""
+        c2w, aux = self.query_batch(img[None], mask[None], k)
+        return c2w[0], aux[0]

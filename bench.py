@@ -6,8 +6,10 @@
 
 Workload (config.workload): BASELINE.json configs[2] -- a synthetic 1M-Gaussian scene (every valid
 ellipsoid casts rays, ~29 rays each), one 1080x1920 query image, bf16 key cache scored on the
-tcgen05 path, fp32 LS solve.  A "step" is one pose query: image -> backbone tokens -> q -> two
-streaming passes over the key cache -> top-100 -> fused LS pose tail -> c2w.  Scene preparation
+tcgen05 path, fp32 LS solve.  A "step" is one batch of `--batch` (default 8) pose queries, each with its own
+image: images -> backbone tokens -> q (once per batch; latency-bound, so 8 images cost about one) and then per
+query two streaming passes over the key cache -> top-100 -> fused LS pose tail -> c2w.  `value` counts
+QUERIES per second; `latency_b1` in the same line is the one-query-per-step figure.  Scene preparation
 (ray generation + key cache) is per scene, not per query, and is reported separately.
 
   value     queries/s, image already resident in HBM, whole query captured in one CUDA graph
@@ -54,6 +56,9 @@ def parse():
     ap.add_argument("--cpu-sample-ellipsoids", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--batch", type=int, default=8,
+                    help="queries per step: the image front end (resize, backbone, q projection, up head) runs once per "
+                         "batch, the key cache is streamed per query; 1 = one query per step")
     return ap.parse_args()
 
 
@@ -231,7 +236,7 @@ def workload_config(args, n_rays, n_rays_local):
     return {"workload": f"{args.gaussians} synthetic Gaussians (all valid ellipsoids, uncapped), {args.height}x{args.width} "
                         f"image, {args.score_impl} key cache, fp32 LS solve (BASELINE.json configs[2])",
             "gaussians": args.gaussians, "n_rays": n_rays, "n_rays_per_rank": n_rays_local, "image": [args.height, args.width],
-            "n_img_tokens": 256, "score_impl": args.score_impl, "backbone": args.backbone, "backbone_matmul": args.backbone_matmul,
+            "n_img_tokens": 256, "queries_per_step": args.batch, "score_impl": args.score_impl, "backbone": args.backbone, "backbone_matmul": args.backbone_matmul,
             "parallelism": f"ray-shard x{args.gpus}", "l2": "inputs larger than L2 (key cache >> 126 MB), no flush needed"}
 
 
@@ -285,13 +290,33 @@ def main():
         n_total = int(t.item())
     est = sharding.ShardedPoseEstimator(idm, ori, dirs, cache, rank, world)
 
-    img_u8 = (sx.synthetic.synth_image(args.height, args.width, seed=7) * 255).to(torch.uint8)
+    B = args.batch
+    img_u8 = torch.stack([(sx.synthetic.synth_image(args.height, args.width, seed=7 + i) * 255).to(torch.uint8) for i in range(B)])
     img_host = img_u8.pin_memory()
     img_dev = (img_u8.to(dev).float() / 255.0).contiguous()
-    mask_dev = torch.ones(args.height, args.width, dtype=torch.bool, device=dev)
+    mask_dev = torch.ones(B, args.height, args.width, dtype=torch.bool, device=dev)
 
     def query():
-        return est.query(img_dev, mask_dev)
+        return est.query_batch(img_dev, mask_dev)
+
+    # one-query-per-step latency figure (eager + its own graphs), measured before the batched graphs are captured
+    lat_b1 = None
+    if B > 1:
+        for _ in range(3):
+            est.query_batch(img_dev[:1], mask_dev[:1])
+        if not args.no_graph:
+            est.enable_cuda_graphs(img_dev[:1].clone(), mask_dev[:1].clone())
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(10):
+            est.query_batch(img_dev[:1], mask_dev[:1])
+        l1.record()
+        torch.cuda.synchronize()
+        lat_b1 = l0.elapsed_time(l1) / 10
+        est._g = None
 
     # ---------------- warm-up, optional CUDA graph ----------------
     for _ in range(max(args.warmup, 3)):
@@ -337,10 +362,10 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = args.steps / (ms / 1e3)
+    value = B * args.steps / (ms / 1e3)
 
     # ---------------- e2e: host image -> pose on host, through the public API ----------------
-    pose_host = torch.empty(4, 4).pin_memory()
+    pose_host = torch.empty(B, 4, 4).pin_memory()
 
     img_e2e = torch.empty_like(img_dev)
 
@@ -348,7 +373,7 @@ def main():
         d = img_host.to(dev, non_blocking=True)
         torch.div(d, 255.0, out=img_e2e)  # uint8 -> [0,1] float (test.py:69-73)
         m = torch.ones_like(img_e2e[..., 0], dtype=torch.bool)
-        c, _ = est.query(img_e2e, m)
+        c, _ = est.query_batch(img_e2e, m)
         pose_host.copy_(c, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -367,8 +392,8 @@ def main():
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e = {"value": args.steps / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": int(img_host.numel()),
-           "d2h_bytes_per_step": 64, "ms_per_step": e2e_ms / args.steps}
+    e2e = {"value": B * args.steps / (e2e_ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": int(img_host.numel()),
+           "d2h_bytes_per_step": 64 * B, "ms_per_step": e2e_ms / args.steps}
 
     # ---------------- roofline of the ray-score kernels (CUDA events around each launch) ----------------
     # sustained = right after the timed regions (same thermal / power-cap state as the timed steps);
@@ -410,11 +435,12 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if "bf16" in args.score_impl else "f32",
                 "data": "synthetic", "config": workload_config(args, n_total, n_local), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": est.launches_per_query * args.steps, "cuda_graph": bool(graph),
+                "gpu_launches": est.launches_per_query * args.steps * B, "cuda_graph": bool(graph),
+                "queries_per_step": B, "latency_b1": {"ms_per_query": lat_b1, "queries_per_s": (1e3 / lat_b1) if lat_b1 else None},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "prepare": {"scene_to_gpu_s": t1 - t0, "raygen_s": t2 - t1, "key_cache_s": t3 - t2,
                             "rays_per_s_raygen": n_local / max(t2 - t1, 1e-9)},
-                "pose": {"centre": [float(x) for x in c2w[:3, 3].tolist()], "status": int(aux[7].item())}}
+                "pose": {"centre": [float(x) for x in c2w[0, :3, 3].tolist()], "status": int(aux[0, 7].item())}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -364,6 +364,19 @@ def test_fused_query_dense_tokens_equals_compacted(sx, module_fp32):
         est = sx.ShardedPoseEstimator(module_fp32, ori, dirs, module_fp32._cache_for(ori, dirs, rgb))
         c2w, _ = est.query(img, mask)
         torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
+    # a batch of different images / masks: front end once, scoring per query; each pose equals its single query
+    img_b = torch.stack((img, img.flip(0), img * 0.5))
+    mask_b = torch.stack((torch.ones(64, 64, dtype=torch.bool, device=DEV), cu(g["mask2"]), cu(g["mask2"]).flip(1)))
+    est = sx.ShardedPoseEstimator(module_fp32, ori, dirs, module_fp32._cache_for(ori, dirs, rgb))
+    c_b, a_b = est.query_batch(img_b, mask_b)
+    for i in range(3):
+        c_i, _ = est.query(img_b[i], mask_b[i])
+        torch.testing.assert_close(c_b[i], c_i, rtol=1e-5, atol=1e-5)
+    assert not torch.allclose(c_b[0], c_b[1])
+    # the same batch through CUDA graphs
+    assert est.enable_cuda_graphs(img_b, mask_b)
+    c_g, _ = est.query_batch(img_b, mask_b)
+    torch.testing.assert_close(c_g, c_b, rtol=1e-5, atol=1e-5)
 
 
 def test_ray_features_tf32_tensor_core_vs_fp32(sx, module_fp32):

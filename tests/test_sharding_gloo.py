@@ -28,8 +28,10 @@ class OracleBackend:
     def __init__(self, oracle, weights, tok_pe, up):
         self.o, self.w, self.tok_pe, self.up = oracle, weights, tok_pe, up
 
-    def tokens(self, img, mask):
-        return self.tok_pe, None, None
+    def tokens(self, imgs, masks):
+        # query i of the batch sees the fixture tokens scaled by (1 + 0.05 i): distinct queries, same rays
+        nb = imgs.shape[0]
+        return torch.stack([self.tok_pe * (1.0 + 0.05 * i) for i in range(nb)]), None, None
 
     def project(self, tok_pe):
         return torch.nn.functional.linear(tok_pe, self.w["attention.q_proj.weight"], self.w["attention.q_proj.bias"])
@@ -56,14 +58,14 @@ class OracleBackend:
         return t.values, t.indices
 
     def camera_up(self, grid):
-        return self.up
+        return self.up[None].expand(8, -1)
 
     def pose_tail(self, ori, dirs, idx, vals, up):
         c2w, aux = self.o.pose_tail(idx, vals, ori, dirs, up)
-        return c2w, aux
+        return c2w, torch.zeros(8)
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, nb=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -84,8 +86,8 @@ def _worker(rank, world, port, out_path):
     cache = sx.RayKeyCache(keys, hi - lo, ())
     be = OracleBackend(oracle, w, g["tok_pe"], g["up"])
     est = sx.ShardedPoseEstimator(None, ori[lo:hi].contiguous(), dirs[lo:hi].contiguous(), cache, rank, world, backend=be)
-    c2w, _ = est.query(None, None, k=100)
-    # every rank must hold the same pose
+    c2w, _ = est.query_batch(torch.zeros(nb, 2, 2, 3), torch.ones(nb, 2, 2, dtype=torch.bool), k=100)
+    # every rank must hold the same poses
     gathered = [torch.empty_like(c2w) for _ in range(world)]
     dist.all_gather(gathered, c2w)
     assert all(torch.equal(gathered[0], x) for x in gathered)
@@ -98,12 +100,21 @@ def _worker(rank, world, port, out_path):
 def test_two_rank_sharded_query_matches_single_process(oracle, synthetic, tmp_path):
     from conftest import load_golden
     out = str(tmp_path / "c2w.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, 3), nprocs=2, join=True)
     c2w = torch.load(out)
+    assert c2w.shape == (3, 4, 4)
     g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
-    top_idx, top_vals = g["topk_idx"], g["topk_vals"]
-    ref, _ = oracle.pose_tail(top_idx, top_vals, r["ori"], r["dirs"], g["up"])
-    torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
+    ref, _ = oracle.pose_tail(g["topk_idx"], g["topk_vals"], r["ori"], r["dirs"], g["up"])
+    torch.testing.assert_close(c2w[0], ref, rtol=1e-5, atol=1e-5)
+    # the other queries of the batch (scaled tokens) against the unsharded oracle
+    w = synthetic.synth_id_weights(seed=g["weight_seed"])
+    fea = oracle.ray_features(r["ori"], r["dirs"], r["rgb"], w)
+    for i in (1, 2):
+        score, _ = oracle.attention_scores(g["tok_pe"] * (1.0 + 0.05 * i), fea, w, return_map=False)
+        top = torch.topk(score, 100)
+        ref_i, _ = oracle.pose_tail(top.indices, top.values, r["ori"], r["dirs"], g["up"])
+        torch.testing.assert_close(c2w[i], ref_i, rtol=1e-4, atol=1e-4)
+        assert not torch.allclose(c2w[i], c2w[0])
 
 
 def test_single_rank_path_uses_no_collective(sx, oracle, synthetic):
@@ -114,6 +125,6 @@ def test_single_rank_path_uses_no_collective(sx, oracle, synthetic):
                                       w["attention.k_proj.weight"], w["attention.k_proj.bias"])
     est = sx.ShardedPoseEstimator(None, r["ori"], r["dirs"], sx.RayKeyCache(keys, keys.shape[0], ()), 0, 1,
                                   backend=OracleBackend(oracle, w, g["tok_pe"], g["up"]))
-    c2w, _ = est.query(None, None)
+    c2w, _ = est.query(torch.zeros(2, 2, 3), torch.ones(2, 2, dtype=torch.bool))
     ref, _ = oracle.pose_tail(g["topk_idx"], g["topk_vals"], r["ori"], r["dirs"], g["up"])
     torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
