@@ -19,6 +19,8 @@ def degrade_mask(scaling_raw: torch.Tensor, target_points: int = 50) -> Tuple[to
     n = s.shape[0]
     valid = torch.empty(n, dtype=torch.uint8, device=s.device)
     rings = torch.empty(n, dtype=torch.int32, device=s.device)
+    if n == 0:  # empty tensors have a null data pointer, which the C ABI rejects by design
+        return valid.bool(), rings
     call("sixdgs_degrade_mask", dptr(s), n, target_points, dptr(valid, torch.uint8), dptr(rings, torch.int32), stream_ptr())
     return valid.bool(), rings
 
@@ -37,6 +39,8 @@ def sym_eig3x3(A: torch.Tensor, eigenvectors: bool = True, eps: Optional[float] 
     n = a.shape[0]
     vals = torch.empty(n, 3, dtype=torch.float32, device=a.device)
     vecs = torch.empty(n, 3, 3, dtype=torch.float32, device=a.device) if eigenvectors else None
+    if n == 0:
+        return vals, vecs
     call("sixdgs_sym_eig3x3", dptr(a), n, ctypes.c_float(eps or 0.0), dptr(vals), dptr(vecs), stream_ptr())
     return vals, vecs
 
@@ -120,6 +124,8 @@ def ray_features(ori, dirs, rgb, pw: Dict[str, torch.Tensor], k_dtype: Optional[
     if k_dtype is not None:
         k_out = torch.empty(n, FEAT, dtype=torch.float32 if k_dtype == F32 else torch.bfloat16, device=dev)
     feat = torch.empty(n, FEAT, dtype=torch.float32, device=dev) if want_features else None
+    if n == 0:
+        return k_out, feat
     wsz = int(_lib.load().sixdgs_ray_features_workspace(n))
     ws = torch.empty(wsz, dtype=torch.uint8, device=dev)
     sfx = "_tf32" if impl == FEATURES_TC else ""
@@ -210,6 +216,8 @@ def topk(scores: torch.Tensor, k: int):
 def line_intersect(points: torch.Tensor, dirs: torch.Tensor, weights: Optional[torch.Tensor] = None):
     p, d = f32c(points), f32c(dirs)
     w = f32c(weights) if weights is not None else None
+    if p.shape[0] == 0:  # no rays: R = 0, det < 1e-7 -> the reference's NaN vector (line_intersection.py:139-142)
+        return torch.full((3,), float("nan"), device=p.device), torch.ones(1, dtype=torch.int32, device=p.device)
     centre = torch.empty(3, dtype=torch.float32, device=p.device)
     status = torch.zeros(1, dtype=torch.int32, device=p.device)
     ws = torch.empty(12, dtype=torch.float64, device=p.device)

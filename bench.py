@@ -327,7 +327,7 @@ def main():
     if not args.no_graph:
         graph = est.enable_cuda_graphs(img_dev, mask_dev)
         if graph:
-            g_out = est.query(img_dev, mask_dev)
+            g_out = est.query_batch(img_dev, mask_dev)
             torch.cuda.synchronize()
             if not torch.allclose(g_out[0], c2w, atol=1e-5, equal_nan=True):
                 print("[bench] CUDA graph replay does not reproduce the eager pose; timing eager launches", file=sys.stderr)
