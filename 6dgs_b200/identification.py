@@ -12,8 +12,12 @@ a query is then two streaming passes over K (per-token softmax statistics, then 
 top-k and one fused pose-tail launch.  The [n_img, n_rays] attention map is only materialised when it
 is small (``attention_map_bytes_limit``); a 1M-Gaussian scene would need 30 GB.
 
-Training (autograd through the kernels) is out of scope for this path: calling
-``forward`` with gradients enabled on trainable parameters raises.
+Training (SURVEY §8b "Autograd", §8f-3): the kernels have no backward.  When gradients are required
+(``torch.is_grad_enabled()`` and trainable hot-path parameters) ``run_attention`` / ``forward`` evaluate the
+same formulas with differentiable torch ops on the same CUDA device (``_run_attention_autograd``), so the
+reference's ``train_id_module`` keeps working; this is the training-mode implementation, not a fallback
+for a missing extension -- it refuses CPU tensors and still requires libsixdgs.so to be loadable.  The
+query path (``test_image`` / ``query_pose`` / ``ShardedPoseEstimator``) never takes it.
 """
 from __future__ import annotations
 
@@ -187,9 +191,7 @@ class IdentificationModule(torch.nn.Module):
         """-> (score[n], attention_map[n_img,n] or None, features_img_flat[n_img,384], camera_up_dir[3])
         (identification_module.py:77-92)."""
         if torch.is_grad_enabled() and any(p.requires_grad for lin in self._hot_params() for p in lin.parameters()):
-            raise NotImplementedError(
-                "autograd through the sm_100a kernels is out of scope for the pose-query path (SURVEY §8f-3); "
-                "call under torch.no_grad() / test_image(), or freeze the module (requires_grad_(False))")
+            return self._run_attention_autograd(img, mask, rays_ori, rays_dir, rays_rgb)
         with torch.no_grad():
             tok_pe, tok, grid = self.backbone_wrapper(img, mask)
             cache = self._cache_for(rays_ori, rays_dir, rays_rgb)
@@ -197,6 +199,29 @@ class IdentificationModule(torch.nn.Module):
             score, amap, _ = self.score_tokens(tok_pe, cache, want_map)
             up = self._camera_up(grid)
         return score, amap, tok, up
+
+    def _run_attention_autograd(self, img, mask, rays_ori, rays_dir, rays_rgb):
+        """Differentiable training-mode evaluation of run_attention (identification_module.py:77-92) with torch
+        ops: PE -> MLP -> k_proj, q_proj, softmax over rays, sum over tokens.  CUDA tensors only."""
+        from . import _lib
+
+        _lib.load()  # the package never runs without its extension, training mode included
+        if not rays_ori.is_cuda:
+            raise _lib.SixdgsError("rays must be CUDA tensors (this package has no CPU path)")
+        lin = torch.nn.functional.linear
+        tok_pe, tok, grid = self.backbone_wrapper(img, mask)
+
+        def pe(p, nf):
+            ang = (p[..., None] * (2.0 ** torch.arange(nf, device=p.device, dtype=p.dtype))).reshape(p.shape[0], -1)
+            return torch.cat((torch.sin(ang), torch.cos(ang)), -1)
+
+        rp = self.ray_preprocessor
+        x = torch.cat((rays_ori, rays_dir, rays_rgb, pe(rays_ori, rp.pospe), pe(rays_dir, rp.viewpe), pe(rays_rgb, rp.rgbpe)), -1)
+        fea = rp.mlp2(torch.cat((rp.mlp(x), x), -1))
+        q = lin(tok_pe, self.attention.q_proj.weight, self.attention.q_proj.bias)
+        k = lin(fea, self.attention.k_proj.weight, self.attention.k_proj.bias)
+        amap = torch.softmax((q @ k.t()) / (q.shape[-1] ** 0.5), dim=-1)
+        return amap.sum(0), amap, tok, self._camera_up(grid)
 
     def forward(self, img, mask, rays_ori, rays_dir, rays_rgb, rays_to_test: int = -1):
         """Training-shaped variant (identification_module.py:94-115): random ray subset first."""

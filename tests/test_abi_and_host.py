@@ -121,9 +121,10 @@ def test_ply_loader_roundtrip(sx, synthetic, tmp_path):
     torch.testing.assert_close(scene.get_scaling, torch.exp(sc["scaling"]))
 
 
-def test_training_forward_is_explicitly_unsupported(sx, synthetic):
+def test_training_mode_refuses_cpu_tensors(sx, synthetic):
+    """with gradients enabled forward() takes the differentiable torch-op route, which is CUDA-only like the rest"""
     idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone())
     img, mask = torch.rand(32, 32, 3), torch.ones(32, 32, dtype=torch.bool)
     r = torch.rand(10, 3)
-    with pytest.raises(NotImplementedError, match="autograd"):
+    with pytest.raises(sx.SixdgsError, match="CUDA"):
         idm(img, mask, r, r, r)

@@ -455,3 +455,26 @@ def test_heavy_tailed_scene_ray_counts_vs_oracle(sx, synthetic, oracle):
     if ori.shape[0] == o_ori.shape[0]:
         frac = ((ori.cpu() - o_ori).abs().max(dim=1).values <= 1e-5 * (1 + o_ori.abs().max(dim=1).values)).float().mean().item()
         assert frac >= 0.97
+
+
+def test_training_mode_forward_is_differentiable_and_matches_kernels(sx, synthetic):
+    """forward() under autograd (train_id_module's call, pose_estimation/train.py:146-148): same numbers as the
+    kernel path, gradients reach the ray MLP and both projections."""
+    r = load_golden("rays_small.npz")
+    g = load_golden("id_module.npz")
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone(), score_impl="simt_fp32")
+    idm.load_state_dict(synthetic.synth_id_weights(seed=3), strict=False)
+    idm = idm.to(DEV).train()
+    ori, dirs, rgb = cu(r["ori"][:2000]), cu(r["dirs"][:2000]), cu(r["rgb"][:2000])
+    img, mask = cu(g["img"]), torch.ones(64, 64, dtype=torch.bool, device=DEV)
+    torch.manual_seed(0)
+    scores, amap, tok, up, used = idm(img, mask, ori, dirs, rgb, rays_to_test=1500)
+    assert scores.requires_grad and amap.shape == (256, 1500) and used.shape == (1500,)
+    (scores * torch.linspace(0, 1, 1500, device=DEV)).sum().backward()
+    for p in (idm.ray_preprocessor.mlp[0].weight, idm.ray_preprocessor.mlp2[2].weight, idm.attention.q_proj.weight,
+              idm.attention.k_proj.weight):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0
+    with torch.no_grad():
+        s_k, _, _, up_k = idm.run_attention(img, mask, ori[used].contiguous(), dirs[used].contiguous(), rgb[used].contiguous())
+    torch.testing.assert_close(scores.detach(), s_k, rtol=1e-3, atol=1e-8)
+    torch.testing.assert_close(up.detach(), up_k, rtol=1e-4, atol=1e-5)
