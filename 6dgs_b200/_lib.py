@@ -31,6 +31,8 @@ _SIGNATURES = {
     "sixdgs_device_supported": ([], c_i),
     "sixdgs_degrade_mask": ([c_p, c_i64, c_i, c_p, c_p, c_p], c_i),
     "sixdgs_knn_normals": ([c_p, c_i64, c_i64, c_i64, c_i, c_p, c_p], c_i),
+    "sixdgs_knn_grid_workspace": ([c_i64, c_i64], c_sz),
+    "sixdgs_knn_normals_grid": ([c_p, c_i64, c_i64, c_i64, c_i, c_p, ctypes.c_float, c_p, c_p, c_p, c_sz, c_p], c_i),
     "sixdgs_sym_eig3x3": ([c_p, c_i64, ctypes.c_float, c_p, c_p, c_p], c_i),
     "sixdgs_raygen_count": ([c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_i, c_i, c_p, c_p, c_p], c_i),
     "sixdgs_raygen_fill": ([c_p, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p], c_i),

@@ -18,6 +18,7 @@ SOURCES = {
     "api.cu": [],
     "raygen.cu": ["-fmad=false"],
     "normals.cu": ["-fmad=false"],
+    "knn_grid.cu": ["-fmad=false"],
     "features.cu": [],
     "features_tc.cu": [],
     "score_simt.cu": [],

@@ -25,12 +25,44 @@ def degrade_mask(scaling_raw: torch.Tensor, target_points: int = 50) -> Tuple[to
     return valid.bool(), rings
 
 
-def knn_normals(cloud: torch.Tensor, k: int = 20, q_begin: int = 0, q_count: Optional[int] = None) -> torch.Tensor:
+def _knn_grid_layout(c: torch.Tensor, points_per_cell: float = 8.0):
+    """uniform grid over the bounding box: (lo[3], cell edge, dims[3]); one host read of the box"""
+    lo_t, hi_t = torch.aminmax(c, dim=0)
+    box = torch.stack((lo_t, hi_t)).cpu().double()
+    lo, hi = box[0], box[1]
+    ext = (hi - lo).clamp_min(1e-12)
+    m = c.shape[0]
+    h = float((ext.prod() / max(m / points_per_cell, 1.0)) ** (1.0 / 3.0))
+    h = max(h, float(ext.max()) / 1024.0, 1e-12)
+    while True:
+        dims = [int(e // h) + 1 for e in ext.tolist()]
+        if max(dims) <= 1024 and dims[0] * dims[1] * dims[2] <= max(4 * m, 4096):
+            break
+        h *= 1.25
+    return [float(x) for x in lo.tolist()], h, dims
+
+
+def knn_normals(cloud: torch.Tensor, k: int = 20, q_begin: int = 0, q_count: Optional[int] = None,
+                method: str = "auto") -> torch.Tensor:
+    """Exact k-NN normals of rows [q_begin, q_begin+q_count) of `cloud`.  method: "brute" (O(m^2), no setup),
+    "grid" (uniform-grid shell search, same result, O(m)) or "auto" (grid from 4096 points up)."""
     c = f32c(cloud)
     m = c.shape[0]
     q_count = m - q_begin if q_count is None else q_count
     out = torch.empty(q_count, 3, dtype=torch.float32, device=c.device)
-    call("sixdgs_knn_normals", dptr(c), m, q_begin, q_count, k, dptr(out), stream_ptr())
+    if q_count == 0:
+        return out
+    if method == "brute" or (method == "auto" and m < 4096):
+        call("sixdgs_knn_normals", dptr(c), m, q_begin, q_count, k, dptr(out), stream_ptr())
+        return out
+    lo, h, dims = _knn_grid_layout(c)
+    n_cells = dims[0] * dims[1] * dims[2]
+    wsz = int(_lib.load().sixdgs_knn_grid_workspace(m, n_cells))
+    ws = torch.empty(wsz, dtype=torch.uint8, device=c.device)
+    lo_arr = (ctypes.c_float * 3)(*lo)
+    dims_arr = (ctypes.c_int * 3)(*dims)
+    call("sixdgs_knn_normals_grid", dptr(c), m, q_begin, q_count, k, ctypes.cast(lo_arr, ctypes.c_void_p),
+         ctypes.c_float(h), ctypes.cast(dims_arr, ctypes.c_void_p), dptr(out), dptr(ws, torch.uint8), wsz, stream_ptr())
     return out
 
 

@@ -59,6 +59,15 @@ int sixdgs_degrade_mask(const float* scaling_raw, int64_t n, int target_points,
 int sixdgs_knn_normals(const float* cloud, int64_t m, int64_t q_begin, int64_t q_count, int k,
                        float* normals_out, void* stream);
 
+/* Same result on a uniform grid, O(m) instead of O(m^2) (exhaustive shell search, exact).  The caller supplies the
+ * grid: lower corner grid_lo_host[3], cubic cell edge `cell`, cells per axis dims_host[3] (HOST values; every point
+ * must lie inside, points outside are clamped to the border cells which keeps the search exact only if none is).
+ * workspace >= sixdgs_knn_grid_workspace(m, dims[0]*dims[1]*dims[2]). */
+size_t sixdgs_knn_grid_workspace(int64_t m, int64_t n_cells);
+int sixdgs_knn_normals_grid(const float* cloud, int64_t m, int64_t q_begin, int64_t q_count, int k,
+                            const float* grid_lo_host, float cell, const int* dims_host, float* normals_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a5: batched closed-form symmetric 3x3 eigen-decomposition --- pose_estimation/sym_eig_3x3.py:246-307
  * A[n,3,3] -> vals[n,3] ascending, vecs[n,3,3] (eigenvectors as COLUMNS; nullable). */
 int sixdgs_sym_eig3x3(const float* A, int64_t n, float eps, float* vals, float* vecs, void* stream);

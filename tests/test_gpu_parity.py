@@ -478,3 +478,28 @@ def test_training_mode_forward_is_differentiable_and_matches_kernels(sx, synthet
         s_k, _, _, up_k = idm.run_attention(img, mask, ori[used].contiguous(), dirs[used].contiguous(), rgb[used].contiguous())
     torch.testing.assert_close(scores.detach(), s_k, rtol=1e-3, atol=1e-8)
     torch.testing.assert_close(up.detach(), up_k, rtol=1e-4, atol=1e-5)
+
+
+def test_knn_grid_equals_brute_force(sx):
+    """the uniform-grid search is exhaustive: identical normals to the brute-force kernel (same neighbour sets,
+    same order), on isotropic, anisotropic, flat and duplicated clouds, for full and partial query ranges."""
+    gen = torch.Generator().manual_seed(17)
+    clouds = {
+        "gauss": torch.randn(30_000, 3, generator=gen),
+        "aniso": torch.randn(20_000, 3, generator=gen) * torch.tensor([20.0, 1.0, 0.05]),
+        "flat": torch.cat((torch.rand(15_000, 2, generator=gen), torch.zeros(15_000, 1)), 1),
+    }
+    dup = torch.randn(12_000, 3, generator=gen)
+    dup[:3000] = dup[3000:6000]
+    clouds["dup"] = dup
+    for name, c in clouds.items():
+        c = c.to(DEV)
+        a = sx.ops.knn_normals(c, 20, method="brute")
+        b = sx.ops.knn_normals(c, 20, method="grid")
+        same = ((a - b).abs().max(dim=1).values == 0).float().mean().item()
+        assert same >= 0.9999, (name, same)
+        part = sx.ops.knn_normals(c, 20, 1000, 5000, method="grid")
+        assert torch.equal(part, b[1000:6000]), name
+    g = load_golden("normals.npz")
+    n = sx.ops.knn_normals(torch.cat((g["cloud"], g["cloud"][:300] + 50.0)).to(DEV)[:600].contiguous(), 20, 0, 300, method="grid").cpu()
+    assert ((n - g["normals"]).abs().max(dim=1).values < 1e-4).float().mean().item() >= 0.99

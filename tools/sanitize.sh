@@ -5,9 +5,8 @@
 set -u
 OUT=gpurun_out/sanitizer_r1.log
 : > $OUT
-run() { echo "=== $*" | tee -a $OUT; timeout -k 10 600 "$@" 2>&1 | grep -E "ERROR SUMMARY|passed|failed|Error|error:|hazard|Invalid" | head -20 | tee -a $OUT; }
+run() { echo "=== $*" | tee -a $OUT; timeout -k 10 200 "$@" 2>&1 | grep -E "ERROR SUMMARY|passed|failed|Error|error:|hazard|Invalid" | head -20 | tee -a $OUT; }
 K="degrade or quadricell or sym_eig or knn or generate_rays_vs_reference or topk or line_intersection or pose_tail or edge_cases"
 run compute-sanitizer --tool memcheck --error-exitcode 0 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "$K" --timeout 550 -x
 run compute-sanitizer --tool memcheck --error-exitcode 0 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "score_tc_vs_torch and (100-256 or 256-7) or tf32" --timeout 550 -x
 run compute-sanitizer --tool racecheck --error-exitcode 0 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "quadricell or topk_against or pose_tail or line_intersection" --timeout 550 -x
-run compute-sanitizer --tool initcheck --error-exitcode 0 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "ray_features_scores_topk or masked_query" --timeout 550 -x
