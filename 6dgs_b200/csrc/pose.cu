@@ -114,9 +114,9 @@ __global__ void ls_solve_kernel(const double* __restrict__ acc, float* __restric
 constexpr int kPoseMaxK = 1024;
 
 __global__ void __launch_bounds__(128)
-pose_tail_kernel(const float* __restrict__ rays_ori, const float* __restrict__ rays_dir, const int64_t* __restrict__ idx,
-                 const float* __restrict__ vals, int k, const float* __restrict__ up, float* __restrict__ c2w,
-                 float* __restrict__ aux) {
+pose_tail_kernel(const float* __restrict__ rays_ori, const float* __restrict__ rays_dir, int64_t ray_stride,
+                 const int64_t* __restrict__ idx, const float* __restrict__ vals, int k, const float* __restrict__ up,
+                 float* __restrict__ c2w, float* __restrict__ aux) {
   __shared__ float so[kPoseMaxK][3], sd[kPoseMaxK][3], sw[kPoseMaxK];
   __shared__ unsigned char once[kPoseMaxK], keep[kPoseMaxK];
   __shared__ int s_n;
@@ -126,8 +126,8 @@ pose_tail_kernel(const float* __restrict__ rays_ori, const float* __restrict__ r
   const int t = threadIdx.x;
   for (int i = t; i < k; i += blockDim.x) {
     const int64_t r = idx[i];
-    so[i][0] = rays_ori[r * 3]; so[i][1] = rays_ori[r * 3 + 1]; so[i][2] = rays_ori[r * 3 + 2];
-    sd[i][0] = rays_dir[r * 3]; sd[i][1] = rays_dir[r * 3 + 1]; sd[i][2] = rays_dir[r * 3 + 2];
+    so[i][0] = rays_ori[r * ray_stride]; so[i][1] = rays_ori[r * ray_stride + 1]; so[i][2] = rays_ori[r * ray_stride + 2];
+    sd[i][0] = rays_dir[r * ray_stride]; sd[i][1] = rays_dir[r * ray_stride + 1]; sd[i][2] = rays_dir[r * ray_stride + 2];
     sw[i] = vals[i];
   }
   __syncthreads();
@@ -286,10 +286,38 @@ extern "C" int sixdgs_line_intersect(const float* points, const float* dirs, con
   return check_launch("line_intersect");
 }
 
-extern "C" int sixdgs_pose_tail(const float* rays_ori, const float* rays_dir, const int64_t* idx, const float* vals,
-                                int k, const float* up, float* c2w, float* aux, void* stream) {
+extern "C" int sixdgs_pose_tail(const float* rays_ori, const float* rays_dir, int64_t ray_stride, const int64_t* idx,
+                                const float* vals, int k, const float* up, float* c2w, float* aux, void* stream) {
   SIXDGS_REQUIRE(rays_ori && rays_dir && idx && vals && up && c2w, "null pointer");
   SIXDGS_REQUIRE(k >= 1 && k <= kPoseMaxK, "k must be in [1, 1024]");
-  pose_tail_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(rays_ori, rays_dir, idx, vals, k, up, c2w, aux);
+  SIXDGS_REQUIRE(ray_stride >= 3, "ray_stride must be >= 3 floats");
+  pose_tail_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(rays_ori, rays_dir, ray_stride, idx, vals, k, up, c2w, aux);
   return check_launch("pose_tail");
+}
+
+// candidate rows for the cross-rank top-k exchange: out[i] = (score, ori3, dir3) of the i-th local winner,
+// rows i >= k_local are (-inf, 0...) so they can never be selected
+__global__ void gather_candidates_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx, int k_local, int k,
+                                         const float* __restrict__ ori, const float* __restrict__ dir,
+                                         float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  float* o = out + (int64_t)i * 7;
+  if (i < k_local) {
+    const int64_t r = idx[i];
+    o[0] = vals[i];
+    o[1] = ori[r * 3]; o[2] = ori[r * 3 + 1]; o[3] = ori[r * 3 + 2];
+    o[4] = dir[r * 3]; o[5] = dir[r * 3 + 1]; o[6] = dir[r * 3 + 2];
+  } else {
+    o[0] = -INFINITY;
+    for (int j = 1; j < 7; ++j) o[j] = 0.f;
+  }
+}
+
+extern "C" int sixdgs_gather_candidates(const float* vals, const int64_t* idx, int k_local, int k, const float* rays_ori,
+                                        const float* rays_dir, float* out, void* stream) {
+  SIXDGS_REQUIRE(out && (k_local == 0 || (vals && idx && rays_ori && rays_dir)), "null pointer");
+  SIXDGS_REQUIRE(k >= 1 && k_local >= 0 && k_local <= k, "bad k");
+  gather_candidates_kernel<<<(k + 127) / 128, 128, 0, (cudaStream_t)stream>>>(vals, idx, k_local, k, rays_ori, rays_dir, out);
+  return check_launch("gather_candidates");
 }

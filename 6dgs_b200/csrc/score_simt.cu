@@ -119,18 +119,23 @@ score_simt_kernel(const TK* __restrict__ kc, int64_t n_rays, const float* __rest
 }
 
 // log-sum-exp merge of partial (max, sum-exp) rows; also merges the rows gathered from other ranks
+// Rows are read in `n_groups` groups of `n_parts` consecutive rows, group g starting at row g * group_stride: lets one
+// query pick its rows out of an all-gathered [rank][query][part] table without a copy.
 __global__ void score_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_z, int n_parts,
-                                   int n_img, const uint8_t* __restrict__ token_valid, float* __restrict__ m,
-                                   float* __restrict__ z) {
+                                   int n_groups, int64_t group_stride, int n_img, const uint8_t* __restrict__ token_valid,
+                                   float* __restrict__ m, float* __restrict__ z) {
   const int t = threadIdx.x;
   if (t >= kMaxTokens) return;
   float mx = -INFINITY;
-  for (int p = 0; p < n_parts; ++p) mx = fmaxf(mx, part_m[(int64_t)p * kMaxTokens + t]);
+  for (int g = 0; g < n_groups; ++g)
+    for (int p = 0; p < n_parts; ++p) mx = fmaxf(mx, part_m[(g * group_stride + p) * kMaxTokens + t]);
   double acc = 0.0;
-  for (int p = 0; p < n_parts; ++p) {
-    const float pm = part_m[(int64_t)p * kMaxTokens + t];
-    if (pm != -INFINITY) acc += (double)part_z[(int64_t)p * kMaxTokens + t] * (double)expf(pm - mx);
-  }
+  for (int g = 0; g < n_groups; ++g)
+    for (int p = 0; p < n_parts; ++p) {
+      const int64_t row = g * group_stride + p;
+      const float pm = part_m[row * kMaxTokens + t];
+      if (pm != -INFINITY) acc += (double)part_z[row * kMaxTokens + t] * (double)expf(pm - mx);
+    }
   // masked-out tokens get (m, z) = (+inf, +inf): exp(L - inf) / inf == 0 in pass 2 whatever L is
   const bool live = (t < n_img) && (token_valid == nullptr || token_valid[t] != 0);
   m[t] = live ? mx : INFINITY;
@@ -174,10 +179,12 @@ int score_simt_parts() { return kSimtParts; }
 
 using namespace sixdgs;
 
-extern "C" int sixdgs_score_merge(const float* part_m, const float* part_z, int n_parts, int n_img,
-                                  const uint8_t* token_valid, float* m, float* z, void* stream) {
+extern "C" int sixdgs_score_merge(const float* part_m, const float* part_z, int n_parts, int n_groups,
+                                  int64_t group_stride, int n_img, const uint8_t* token_valid, float* m, float* z,
+                                  void* stream) {
   SIXDGS_REQUIRE(part_m && part_z && m && z, "null pointer");
-  SIXDGS_REQUIRE(n_parts > 0 && n_img > 0 && n_img <= kMaxTokens, "bad size");
-  score_merge_kernel<<<1, kMaxTokens, 0, (cudaStream_t)stream>>>(part_m, part_z, n_parts, n_img, token_valid, m, z);
+  SIXDGS_REQUIRE(n_parts > 0 && n_groups > 0 && group_stride >= 0 && n_img > 0 && n_img <= kMaxTokens, "bad size");
+  score_merge_kernel<<<1, kMaxTokens, 0, (cudaStream_t)stream>>>(part_m, part_z, n_parts, n_groups, group_stride, n_img,
+                                                                 token_valid, m, z);
   return check_launch("score_merge");
 }

@@ -216,11 +216,16 @@ def score_pass1(k_cache: torch.Tensor, q: torch.Tensor, impl: int = SCORE_SIMT):
     return pm, pz
 
 
-def score_merge(pm: torch.Tensor, pz: torch.Tensor, n_img: int, token_valid: Optional[torch.Tensor] = None):
+def score_merge(pm: torch.Tensor, pz: torch.Tensor, n_img: int, token_valid: Optional[torch.Tensor] = None,
+                rows: Optional[int] = None, groups: int = 1, group_stride: int = 0, first_row: int = 0):
+    """merge `groups` groups of `rows` consecutive partial rows (group g starts at first_row + g*group_stride);
+    default: all rows of pm/pz."""
     m = torch.empty(MAX_TOKENS, dtype=torch.float32, device=pm.device)
     z = torch.empty(MAX_TOKENS, dtype=torch.float32, device=pm.device)
-    call("sixdgs_score_merge", dptr(pm), dptr(pz), pm.shape[0], n_img, dptr(token_valid, torch.uint8), dptr(m), dptr(z),
-         stream_ptr())
+    rows = pm.shape[0] if rows is None else rows
+    off = first_row * MAX_TOKENS * 4
+    call("sixdgs_score_merge", dptr(pm) + off, dptr(pz) + off, rows, groups, group_stride, n_img,
+         dptr(token_valid, torch.uint8), dptr(m), dptr(z), stream_ptr())
     return m, z
 
 
@@ -261,6 +266,23 @@ def line_intersect(points: torch.Tensor, dirs: torch.Tensor, weights: Optional[t
 def pose_tail(rays_ori, rays_dir, idx, vals, up):
     c2w = torch.empty(4, 4, dtype=torch.float32, device=rays_ori.device)
     aux = torch.empty(8, dtype=torch.float32, device=rays_ori.device)
-    call("sixdgs_pose_tail", dptr(rays_ori), dptr(rays_dir), dptr(idx, torch.int64), dptr(vals), idx.shape[0],
+    call("sixdgs_pose_tail", dptr(rays_ori), dptr(rays_dir), 3, dptr(idx, torch.int64), dptr(vals), idx.shape[0],
          dptr(f32c(up)), dptr(c2w), dptr(aux), stream_ptr())
     return c2w, aux
+
+
+def pose_tail_candidates(cand: torch.Tensor, idx, vals, up):
+    """pose tail straight from a packed candidate table [n,7] = (score, ori3, dir3) (no slicing copies)"""
+    c2w = torch.empty(4, 4, dtype=torch.float32, device=cand.device)
+    aux = torch.empty(8, dtype=torch.float32, device=cand.device)
+    base = dptr(cand)
+    call("sixdgs_pose_tail", base + 4, base + 16, 7, dptr(idx, torch.int64), dptr(vals), idx.shape[0], dptr(f32c(up)),
+         dptr(c2w), dptr(aux), stream_ptr())
+    return c2w, aux
+
+
+def gather_candidates(vals, idx, rays_ori, rays_dir, k: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    out = out if out is not None else torch.empty(k, 7, dtype=torch.float32, device=rays_ori.device)
+    call("sixdgs_gather_candidates", dptr(vals), dptr(idx, torch.int64), idx.shape[0], k, dptr(rays_ori), dptr(rays_dir),
+         dptr(out), stream_ptr())
+    return out

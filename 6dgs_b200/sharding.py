@@ -42,8 +42,14 @@ class CudaBackend:
     def pass1(self, keys, q):
         return ops.score_pass1(keys, q, self.impl)
 
-    def merge(self, pm, pz, n_img, valid=None):
-        return ops.score_merge(pm, pz, n_img, valid)
+    def merge(self, pm, pz, n_img, valid=None, rows=None, groups=1, group_stride=0, first_row=0):
+        return ops.score_merge(pm, pz, n_img, valid, rows, groups, group_stride, first_row)
+
+    def candidates(self, vals, idx, ori, dirs, k, out):
+        return ops.gather_candidates(vals, idx, ori, dirs, k, out)
+
+    def pose_tail_candidates(self, cand, idx, vals, up):
+        return ops.pose_tail_candidates(cand, idx, vals, up)
 
     def pass2(self, keys, q, m, z, out):
         return ops.score_pass2(keys, q, m, z, self.impl, out=out)[0]
@@ -119,35 +125,34 @@ class ShardedPoseEstimator:
         pm/pz are [world * B * rows, 256] (rank-major); query i owns rows [r*B*rows + i*rows, +rows) of every rank r."""
         b = self.backend
         nb, rows = st["nb"], st["rows"]
-        pm = pm.reshape(-1, nb, rows, pm.shape[-1])
-        pz = pz.reshape(-1, nb, rows, pz.shape[-1])
+        groups = pm.shape[0] // (nb * rows)  # == world
         k_local = min(k, self.cache.n_rays)
         vals, idxs = [], []
         cand = None
         if self.world > 1:
-            cand = torch.full((nb, k, 7), float("-inf"), dtype=torch.float32, device=self.ori.device)
+            cand = torch.empty((nb, k, 7), dtype=torch.float32, device=self.ori.device)
         for i in range(nb):
-            m, z = b.merge(pm[:, i].reshape(-1, pm.shape[-1]).contiguous(), pz[:, i].reshape(-1, pz.shape[-1]).contiguous(),
-                           st["n_img"], st["valid"][i] if st["valid"] is not None else None)
+            # query i's rows: [rank g][query i][0..rows) -> group stride nb*rows, first row i*rows (no copies)
+            m, z = b.merge(pm, pz, st["n_img"], st["valid"][i] if st["valid"] is not None else None,
+                           rows=rows, groups=groups, group_stride=nb * rows, first_row=i * rows)
             scores = b.pass2(self.cache.keys, st["q"][i], m, z, self.cache.scores)
             v, ix = b.topk(scores, k_local)
             vals.append(v)
             idxs.append(ix)
             if cand is not None:
-                cand[i, :k_local, 0] = v
-                cand[i, :k_local, 1:4] = self.ori[ix]
-                cand[i, :k_local, 4:7] = self.dirs[ix]
+                b.candidates(v, ix, self.ori, self.dirs, k, cand[i])
         return vals, idxs, cand
 
     def _stage3(self, allc, up, k, nb):
         """allc [world * B, k, 7] (rank-major) -> per-query global top-k -> pose"""
         b = self.backend
         allc = allc.reshape(-1, nb, allc.shape[-2], 7)
+        byq = allc.transpose(0, 1).contiguous()  # [B, world, k, 7]: one copy per batch
         outs = []
         for i in range(nb):
-            c = allc[:, i].reshape(-1, 7)
+            c = byq[i].reshape(-1, 7)
             gvals, gidx = b.topk(c[:, 0].contiguous(), k)
-            outs.append(b.pose_tail(c[:, 1:4].contiguous(), c[:, 4:7].contiguous(), gidx, gvals, up[i]))
+            outs.append(b.pose_tail_candidates(c, gidx, gvals, up[i]))
         return torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
 
     def _query_eager(self, imgs, masks, k):

@@ -131,7 +131,8 @@ size_t sixdgs_score_workspace(int impl);
 int sixdgs_score_pass1(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_img,
                        float* part_m, float* part_z, int impl, void* workspace, size_t workspace_bytes,
                        void* stream);
-int sixdgs_score_merge(const float* part_m, const float* part_z, int n_parts, int n_img,
+int sixdgs_score_merge(const float* part_m, const float* part_z, int n_parts, int n_groups,
+                       int64_t group_stride /* rows between groups; groups of n_parts consecutive rows */, int n_img,
                        const uint8_t* token_valid /* nullable [256]: 0 = token masked out */, float* m,
                        float* z, void* stream);
 int sixdgs_score_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_img,
@@ -155,8 +156,14 @@ int sixdgs_line_intersect(const float* points, const float* dirs, const float* w
  * top-k candidates (idx into rays_ori/rays_dir, vals = scores) + camera up -> c2w[16] row-major.
  * aux (nullable, 8 floats): centre[3], watch[3], n_kept, status (bit0 NaN centre, bit1 singular
  * rotation -> identity, bit2 NaN c2w -> identity).  k <= 1024. */
-int sixdgs_pose_tail(const float* rays_ori, const float* rays_dir, const int64_t* idx,
-                     const float* vals, int k, const float* up, float* c2w, float* aux, void* stream);
+int sixdgs_pose_tail(const float* rays_ori, const float* rays_dir, int64_t ray_stride /* floats between rays, >= 3 */,
+                     const int64_t* idx, const float* vals, int k, const float* up, float* c2w, float* aux,
+                     void* stream);
+
+/* ---- multi-GPU candidate exchange (no reference counterpart): out[k,7] = (score, ori3, dir3) of the local
+ * top-k_local rays, rows >= k_local padded with score -inf. */
+int sixdgs_gather_candidates(const float* vals, const int64_t* idx, int k_local, int k, const float* rays_ori,
+                             const float* rays_dir, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,10 @@ class OracleBackend:
         pad = 256 - m.shape[0]
         return (torch.cat((m, torch.full((pad,), -float("inf"))))[None], torch.cat((z, torch.zeros(pad)))[None])
 
-    def merge(self, pm, pz, n_img, valid=None):
+    def merge(self, pm, pz, n_img, valid=None, rows=None, groups=1, group_stride=0, first_row=0):
+        if rows is not None:
+            sel = torch.cat([torch.arange(first_row + g * group_stride, first_row + g * group_stride + rows) for g in range(groups)])
+            pm, pz = pm[sel], pz[sel]
         m = pm.max(0).values
         z = (pz * torch.exp(pm - m[None])).nan_to_num(0.0).sum(0)
         return m[:n_img], z[:n_img]
@@ -59,6 +62,15 @@ class OracleBackend:
 
     def camera_up(self, grid):
         return self.up[None].expand(8, -1)
+
+    def candidates(self, vals, idx, ori, dirs, k, out):
+        out.fill_(float("-inf"))
+        n = idx.shape[0]
+        out[:n, 0], out[:n, 1:4], out[:n, 4:7] = vals, ori[idx], dirs[idx]
+        return out
+
+    def pose_tail_candidates(self, cand, idx, vals, up):
+        return self.pose_tail(cand[:, 1:4].contiguous(), cand[:, 4:7].contiguous(), idx, vals, up)
 
     def pose_tail(self, ori, dirs, idx, vals, up):
         c2w, aux = self.o.pose_tail(idx, vals, ori, dirs, up)
