@@ -271,11 +271,11 @@ def main():
     ori, dirs, rgb = sx.generate_all_possible_rays(scene, max_ellipsoids=None, shard=(rank, world) if world > 1 else None)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    backbone = sx.synthetic.SyntheticBackbone() if args.backbone == "synthetic" else sx.DinoV2ViTS14()
     import warnings
+    torch.manual_seed(0)  # identical (random-init) backbone / head weights on every rank and every run
+    backbone = sx.synthetic.SyntheticBackbone() if args.backbone == "synthetic" else sx.DinoV2ViTS14()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        torch.manual_seed(0)
         idm = sx.IdentificationModule("dino", backbone=backbone, score_impl=args.score_impl)
     idm.load_state_dict(sx.synthetic.synth_id_weights(seed=3), strict=False)
     idm = idm.to(dev).eval().requires_grad_(False)
