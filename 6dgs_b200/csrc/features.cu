@@ -158,37 +158,31 @@ extern "C" int sixdgs_ray_features(const float* ori, const float* dir, const flo
     pe_kernel<<<(unsigned)((c + 127) / 128), 128, 0, s>>>(ori + r0 * 3, dir + r0 * 3, rgb + r0 * 3, c, X, impl == 1);
     int rc = check_launch("pe");
     if (rc) return rc;
-    // mlp.0: x(144) -> H(512), relu ; mlp.2: H -> X[:, :512], relu
+    // mlp.0: x(160) -> H(512), relu ; mlp.2: H -> X[:, :512], relu
     if ((rc = launch_any<float>(impl, X + 512, c, kInPad, kXW, w1p, b1, 512, H, 512, 1, s))) return rc;
     if ((rc = launch_any<float>(impl, H, c, 512, 512, w2, b2, 512, X, kXW, 1, s))) return rc;
-    // mlp2.0: [h, x](656) -> H(512), relu ; mlp2.2: H -> feature(384)
+    // mlp2.0: [h, x](672) -> H(512), relu
     if ((rc = launch_any<float>(impl, X, c, kXW, kXW, w3p, b3, 512, H, 512, 1, s))) return rc;
     const bool project = (k_out != nullptr) && (wk != nullptr);
-    float* fdst = feat_out ? feat_out + r0 * kFeat : F;
-    if (!project && k_out && !feat_out) {
-      // no projection: the feature itself is the requested output
+    if (k_out && !project) {
+      // no projection requested: the MLP feature itself is the key-shaped output (feat_out must then be NULL)
+      if (feat_out) { set_error("ray_features: k_out without wk requires feat_out == NULL"); return SIXDGS_EINVAL; }
       if (k_dtype == SIXDGS_F32)
         rc = launch_any<float>(impl, H, c, 512, 512, w4, b4, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s, 0);
       else
-        rc = launch_any<__nv_bfloat16>(impl, H, c, 512, 512, w4, b4, kFeat, (__nv_bfloat16*)k_out + r0 * kFeat,
-                                       kFeat, 0, s, 0);
+        rc = launch_any<__nv_bfloat16>(impl, H, c, 512, 512, w4, b4, kFeat, (__nv_bfloat16*)k_out + r0 * kFeat, kFeat, 0, s, 0);
       if (rc) return rc;
       continue;
     }
-    // the feature feeds k_proj when a projection follows; if it is also returned to the caller keep it unrounded
+    // mlp2.2: H -> feature(384).  It feeds k_proj when a projection follows; if the caller also wants the
+    // feature back it stays unrounded (only the last GEMM then sees TF32 truncation on its A operand).
+    float* fdst = feat_out ? feat_out + r0 * kFeat : F;
     if ((rc = launch_any<float>(impl, H, c, 512, 512, w4, b4, kFeat, fdst, kFeat, 0, s, (project && !feat_out) ? 1 : 0))) return rc;
-    if (k_out) {
-      if (project) {
-        if (k_dtype == SIXDGS_F32)
-          rc = launch_any<float>(impl, fdst, c, kFeat, kFeat, wk, bk, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s, 0);
-        else
-          rc = launch_any<__nv_bfloat16>(impl, fdst, c, kFeat, kFeat, wk, bk, kFeat,
-                                         (__nv_bfloat16*)k_out + r0 * kFeat, kFeat, 0, s, 0);
-      } else {
-        // identity "projection" of the stored feature into k_out (dtype conversion only)
-        set_error("ray_features: k_out without wk requires feat_out == NULL");
-        return SIXDGS_EINVAL;
-      }
+    if (project) {
+      if (k_dtype == SIXDGS_F32)
+        rc = launch_any<float>(impl, fdst, c, kFeat, kFeat, wk, bk, kFeat, (float*)k_out + r0 * kFeat, kFeat, 0, s, 0);
+      else
+        rc = launch_any<__nv_bfloat16>(impl, fdst, c, kFeat, kFeat, wk, bk, kFeat, (__nv_bfloat16*)k_out + r0 * kFeat, kFeat, 0, s, 0);
       if (rc) return rc;
     }
   }

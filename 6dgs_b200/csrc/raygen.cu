@@ -73,10 +73,6 @@ __device__ __forceinline__ double warp_scan_incl(double v, int lane) {
   return v;
 }
 
-struct ShBasis {
-  float b[16];
-};
-
 // rgb = max(SH(sh, -dir) + 0.5, 0) with the reference's left-to-right accumulation (sh_utils.py:72-103)
 __device__ __forceinline__ float sh_channel(const float* __restrict__ sh, int ch, int deg, float x, float y, float z) {
   const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
