@@ -532,3 +532,41 @@ def test_two_shard_pipeline_on_one_gpu_equals_unsharded(sx, module_fp32):
     for s, st in zip(shards, sts):
         c2w, aux = s._stage3(allc, st["up"], k, st["nb"])
         torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_full_size_properties_1m_gaussians(sx, synthetic):
+    """BASELINE.json's full size (configs[2]: 1M Gaussians, ~29M rays) through size-independent properties on
+    the tensor-core path: softmax rows sum to one, statistics of shards merge to the statistics of the whole,
+    the radix top-k agrees with torch.topk, and every ray origin lies on its ellipsoid."""
+    scene = sx.GaussianScene.from_dict(synthetic.synth_scene(1_000_000, seed=0, extent=5.0), device=DEV)
+    ori, dirs, rgb, gid = sx.generate_all_possible_rays(scene, max_ellipsoids=None, return_ids=True)
+    n = ori.shape[0]
+    assert 27_000_000 < n < 31_000_000
+    assert torch.allclose(dirs[::997].norm(dim=1), torch.ones_like(dirs[::997, 0]), atol=1e-5)
+    sel = torch.arange(0, n, 4999, device=DEV)
+    q4 = torch.nn.functional.normalize(scene._rotation[gid[sel]])
+    w, x, y, z = q4.unbind(-1)
+    R = torch.stack((1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z),
+                     1 - 2 * (x * x + z * z), 2 * (y * z - w * x), 2 * (x * z - w * y), 2 * (y * z + w * x),
+                     1 - 2 * (x * x + y * y)), -1).reshape(-1, 3, 3)
+    local = (R.transpose(1, 2) @ (ori[sel] - scene._xyz[gid[sel]])[..., None])[..., 0]
+    s = torch.exp(scene._scaling[gid[sel]])
+    unit = torch.stack((local[:, 0] / s[:, 1], local[:, 1] / s[:, 2], local[:, 2] / s[:, 0]), -1).norm(dim=1)
+    assert torch.allclose(unit, torch.ones_like(unit), atol=5e-3)
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone(), score_impl="tc_bf16")
+    idm.load_state_dict(synthetic.synth_id_weights(seed=3), strict=False)
+    idm = idm.to(DEV).eval().requires_grad_(False)
+    cache = idm.build_key_cache(ori, dirs, rgb)
+    tok = torch.randn(256, 398, generator=torch.Generator().manual_seed(2)).to(DEV)
+    scores, _, (m, z) = idm.score_tokens(tok, cache)
+    assert abs(scores.double().sum().item() - 256.0) < 0.3 and torch.isfinite(scores).all()
+    q = sx.ops.project_queries(tok, idm.packed_weights())
+    h = n // 3
+    pm1, pz1 = sx.ops.score_pass1(cache.keys[:h], q, sx.ops.SCORE_TC)
+    pm2, pz2 = sx.ops.score_pass1(cache.keys[h:], q, sx.ops.SCORE_TC)
+    m2, z2 = sx.ops.score_merge(torch.cat((pm1, pm2)), torch.cat((pz1, pz2)), 256)
+    torch.testing.assert_close(m2, m, rtol=0, atol=0)
+    torch.testing.assert_close(z2, z, rtol=1e-4, atol=0)
+    vals, idx = sx.ops.topk(scores, 100)
+    ref = torch.topk(scores, 100)
+    assert torch.equal(vals, ref.values) and torch.equal(scores[idx], vals)
