@@ -439,7 +439,9 @@ def main():
                 "queries_per_step": B, "latency_b1": {"ms_per_query": lat_b1, "queries_per_s": (1e3 / lat_b1) if lat_b1 else None},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "prepare": {"scene_to_gpu_s": t1 - t0, "raygen_s": t2 - t1, "key_cache_s": t3 - t2,
-                            "rays_per_s_raygen": n_local / max(t2 - t1, 1e-9)},
+                            "rays_per_s_raygen": n_local / max(t2 - t1, 1e-9),
+                            # cold = scene preparation (rays + key cache, once per scene / weight update) + one query
+                            "cold_first_query_s": (t3 - t1) + ms / 1e3 / (args.steps * B)},
                 "pose": {"centre": [float(x) for x in c2w[0, :3, 3].tolist()], "status": int(aux[0, 7].item())}}
         print(json.dumps(line))
     if world > 1:
