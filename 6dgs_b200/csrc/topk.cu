@@ -124,6 +124,39 @@ topk_final_kernel(TopkState* st, const uint32_t* __restrict__ ckey, const int64_
   if (t < k) { vals[t] = key2f(skey[t]); idx[t] = sidx[t]; }
 }
 
+// n <= 4096 (e.g. the cross-rank candidate table, world * k rows): one CTA, one launch -- load everything,
+// bitonic sort by (key desc, index asc), emit the first k.  Same ordering as the radix path.
+constexpr int kSmallN = 4096;
+
+__global__ void __launch_bounds__(1024)
+topk_small_kernel(const float* __restrict__ x, int n, int k, float* __restrict__ vals, int64_t* __restrict__ idx) {
+  __shared__ uint32_t skey[kSmallN];
+  __shared__ int sidx[kSmallN];
+  const int t = threadIdx.x;
+  int np = 1;
+  while (np < n) np <<= 1;
+  for (int i = t; i < np; i += blockDim.x) {
+    skey[i] = (i < n) ? f2key(x[i]) : 0u;
+    sidx[i] = (i < n) ? i : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int sz = 2; sz <= np; sz <<= 1)
+    for (int st2 = sz >> 1; st2 > 0; st2 >>= 1) {
+      for (int i = t; i < np; i += blockDim.x) {
+        const int j = i ^ st2;
+        if (j > i) {
+          const bool in_order = ((i & sz) == 0);
+          const uint32_t ka = skey[i], kb = skey[j];
+          const int ia = sidx[i], ib = sidx[j];
+          const bool a_first = (ka > kb) || (ka == kb && ia < ib);
+          if (a_first != in_order) { skey[i] = kb; skey[j] = ka; sidx[i] = ib; sidx[j] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = t; i < k; i += blockDim.x) { vals[i] = key2f(skey[i]); idx[i] = sidx[i]; }
+}
+
 }  // namespace sixdgs
 
 using namespace sixdgs;
@@ -143,6 +176,10 @@ extern "C" int sixdgs_topk(const float* scores, int64_t n, int k, float* vals, i
     return SIXDGS_EWORKSPACE;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (n <= kSmallN) {
+    topk_small_kernel<<<1, 1024, 0, s>>>(scores, (int)n, k, vals, idx);
+    return check_launch("topk_small");
+  }
   unsigned char* w = (unsigned char*)workspace;
   TopkState* st = (TopkState*)w;
   w += sizeof(TopkState);

@@ -207,6 +207,14 @@ def test_topk_against_torch(sx):
     assert torch.equal(vals, torch.topk(x, 300).values) and torch.equal(x[idx], vals)
     lowest = torch.nonzero(x == vals[-1]).squeeze(1)[: int((vals == vals[-1]).sum())]
     assert torch.equal(idx[vals == vals[-1]].sort().values, lowest)
+    # the single-launch small-n path (n <= 4096), ties included
+    xs = (torch.rand(3000, generator=gen) * 10).floor().to(DEV)
+    vals, idx = sx.ops.topk(xs, 300)
+    assert torch.equal(vals, torch.topk(xs, 300).values) and torch.equal(xs[idx], vals)
+    lowest = torch.nonzero(xs == vals[-1]).squeeze(1)[: int((vals == vals[-1]).sum())]
+    assert torch.equal(idx[vals == vals[-1]].sort().values, lowest)
+    one = sx.ops.topk(torch.tensor([3.5], device=DEV), 1)
+    assert one[0].item() == 3.5 and one[1].item() == 0
     with pytest.raises(sx.SixdgsError):
         sx.ops.topk(x[:10], 11)
 
