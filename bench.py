@@ -6,8 +6,8 @@
 
 Workload (config.workload): BASELINE.json configs[2] -- a synthetic 1M-Gaussian scene (every valid
 ellipsoid casts rays, ~29 rays each), one 1080x1920 query image, bf16 key cache scored on the
-tcgen05 path, fp32 LS solve.  A "step" is one batch of `--batch` (default 16) pose queries, each with its own
-image: images -> backbone tokens -> q (once per batch; latency-bound, so 16 images cost little more than one) and then per
+tcgen05 path, fp32 LS solve.  A "step" is one batch of `--batch` (default 8) pose queries, each with its own
+image: images -> backbone tokens -> q (once per batch; latency-bound, so 8 images cost about one) and then per
 query two streaming passes over the key cache -> top-100 -> fused LS pose tail -> c2w.  `value` counts
 QUERIES per second; `latency_b1` in the same line is the one-query-per-step figure.  Scene preparation
 (ray generation + key cache) is per scene, not per query, and is reported separately.
@@ -42,7 +42,7 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gaussians", type=int, default=1_000_000)
@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--cpu-sample-ellipsoids", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--batch", type=int, default=16,
+    ap.add_argument("--batch", type=int, default=8,
                     help="queries per step: the image front end (resize, backbone, q projection, up head) runs once per "
                          "batch, the key cache is streamed per query; 1 = one query per step")
     return ap.parse_args()
