@@ -1,9 +1,12 @@
 // a4 at scale: exact k-NN normals with a uniform grid (reference semantics: pose_estimation/sampling.py:62-113,
 // exact cdist + topk).  Same result as the brute-force kernel in normals.cu -- the search in knn_grid.cuh is
 // provably exhaustive -- at O(M) instead of O(M^2) work: 1M points in tens of milliseconds instead of ~1 s.
-// Pipeline (all stream ordered, no host sync): cell ids + histogram -> exclusive scan -> scatter -> per-cell
-// index sort (deterministic order) -> one thread per query in cell order (neighbouring threads walk the same
-// cells, so the point reads hit L1/L2).
+// Pipeline (all stream ordered, no host sync): cell ids + histogram -> exclusive scan -> scatter -> one thread per
+// query in cell order (neighbouring threads walk the same cells, so the point reads hit L1/L2).  The order of the
+// points inside a cell depends on atomics, the result does not: candidates are ranked by (distance, index), which
+// is independent of the order in which they are visited.  Points outside the grid box (the host may build it from
+// robust statistics so that a few far outliers do not inflate the cells) are clamped into the border cells; the
+// search treats faces on the grid boundary as open, so it stays exhaustive.
 #include "common.cuh"
 #include "normal_fit.cuh"
 #include "knn_grid.cuh"
@@ -28,19 +31,6 @@ __global__ void grid_scatter_kernel(const int* __restrict__ cell_of, int64_t m, 
   if (i >= m) return;
   const int c = cell_of[i];
   sorted_idx[cell_start[c] + atomicAdd(&cursor[c], 1)] = (int)i;
-}
-
-// ascending point index inside every cell: the scatter order depends on atomics, the search result must not
-__global__ void grid_sort_cells_kernel(const int64_t* __restrict__ cell_start, int64_t n_cells, int* __restrict__ sorted_idx) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cells) return;
-  const int64_t a = cell_start[c], b = cell_start[c + 1];
-  for (int64_t i = a + 1; i < b; ++i) {
-    const int v = sorted_idx[i];
-    int64_t j = i;
-    while (j > a && sorted_idx[j - 1] > v) { sorted_idx[j] = sorted_idx[j - 1]; --j; }
-    sorted_idx[j] = v;
-  }
 }
 
 constexpr int kGridMaxK = 32;
@@ -95,7 +85,6 @@ extern "C" int sixdgs_knn_normals_grid(const float* cloud, int64_t m, int64_t q_
   int rc = sixdgs_exclusive_scan(count, n_cells, cell_start, stream);
   if (rc) return rc;
   grid_scatter_kernel<<<pb, 256, 0, s>>>(cell_of, m, cell_start, cursor, sorted_idx);
-  grid_sort_cells_kernel<<<(unsigned)((n_cells + 127) / 128), 128, 0, s>>>(cell_start, n_cells, sorted_idx);
   grid_query_kernel<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(cloud, m, g, cell_start, sorted_idx, q_begin, q_count, k,
                                                              normals_out);
   return check_launch("knn_normals_grid");

@@ -1,8 +1,8 @@
 // Exact k-nearest-neighbour search on a uniform grid (host/device shared core, so the search logic can be
 // unit-tested on the CPU against brute force -- tests/test_knn_grid_host.py compiles this header with g++).
 //
-// Points are bucketed into cubic cells of edge h over the cloud's bounding box (counting sort: cell_start /
-// sorted_idx, indices ascending inside a cell).  A query visits the cells in growing Chebyshev shells around
+// Points are bucketed into cubic cells of edge h over a box around the cloud (counting sort: cell_start /
+// sorted_idx; points outside the box are clamped into the border cells, whose outward faces are treated as open).  A query visits the cells in growing Chebyshev shells around
 // its own cell and stops as soon as its current k-th best distance is no larger than the distance to the
 // surface of the cube of cells already visited -- every unvisited point is at least that far away, so the
 // result is EXACTLY the brute-force answer.  Candidates are ordered by (distance, index), which is the order

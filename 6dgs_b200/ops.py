@@ -26,9 +26,12 @@ def degrade_mask(scaling_raw: torch.Tensor, target_points: int = 50) -> Tuple[to
 
 
 def _knn_grid_layout(c: torch.Tensor, points_per_cell: float = 8.0):
-    """uniform grid over the bounding box: (lo[3], cell edge, dims[3]); one host read of the box"""
+    """uniform grid over a robust box of the cloud: (lo[3], cell edge, dims[3]); one host read of the statistics.
+    The box is the bounding box clipped to mean +- 4 sigma per axis, so a few far outliers (floaters of a real 3DGS
+    scene) do not inflate the cells; points outside are clamped into border cells and the search stays exact."""
     lo_t, hi_t = torch.aminmax(c, dim=0)
-    box = torch.stack((lo_t, hi_t)).cpu().double()
+    mu, sd = c.mean(dim=0), c.std(dim=0)
+    box = torch.stack((torch.maximum(lo_t, mu - 4 * sd), torch.minimum(hi_t, mu + 4 * sd))).cpu().double()
     lo, hi = box[0], box[1]
     ext = (hi - lo).clamp_min(1e-12)
     m = c.shape[0]

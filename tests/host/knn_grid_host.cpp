@@ -7,15 +7,17 @@ using std::max; using std::min;
 #include "knn_grid.cuh"
 using namespace sixdgs;
 int main() {
-  for (int trial = 0; trial < 6; ++trial) {
-    const int m = trial < 3 ? 3000 : 20000, k = 20;
+  for (int trial = 0; trial < 8; ++trial) {
+    const int m = (trial < 3 || trial >= 6) ? 3000 : 20000, k = 20;
     srand(trial + 1);
     std::vector<float> c(m * 3);
     auto rnd = []() { float s = 0; for (int i = 0; i < 6; ++i) s += rand() / (float)RAND_MAX; return (s - 3.f); };
     for (int i = 0; i < m; ++i) { c[i*3] = rnd() * (trial==1?10.f:1.f); c[i*3+1] = rnd(); c[i*3+2] = rnd() * (trial==2?0.01f:1.f); }
     if (trial == 4) for (int i = 0; i < 200; ++i) { c[i*3] = c[(i+200)*3]; c[i*3+1] = c[(i+200)*3+1]; c[i*3+2] = c[(i+200)*3+2]; }  // duplicates
+    if (trial >= 6) for (int i = 0; i < 150; ++i) for (int a = 0; a < 3; ++a) c[i*3+a] *= (trial == 6 ? 50.f : 1000.f);  // far outliers
     KnnGrid g; float lo[3] = {1e30f,1e30f,1e30f}, hi[3] = {-1e30f,-1e30f,-1e30f};
     for (int i = 0; i < m; ++i) for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], c[i*3+a]); hi[a] = std::max(hi[a], c[i*3+a]); }
+    if (trial >= 6) for (int a = 0; a < 3; ++a) { lo[a] = std::max(lo[a], -3.0f); hi[a] = std::min(hi[a], 3.0f); }  // robust box: outliers get clamped
     double vol = 1; for (int a = 0; a < 3; ++a) vol *= std::max(hi[a]-lo[a], 1e-6f);
     g.h = (float)cbrt(vol / (m / 8.0));
     for (int a = 0; a < 3; ++a) { g.lo[a] = lo[a]; g.dim[a] = std::max(1, (int)ceilf((hi[a]-lo[a]) / g.h + 1e-3f)); if (g.dim[a] > 256) g.dim[a] = 256; }

@@ -24,7 +24,7 @@ def test_grid_knn_search_is_exact(tmp_path):
     subprocess.check_call(["g++", "-O2", "-I", CSRC, "-o", exe, os.path.join(ROOT, "tests", "host", "knn_grid_host.cpp")])
     out = subprocess.check_output([exe], text=True)
     lines = [ln for ln in out.splitlines() if ln.startswith("trial")]
-    assert len(lines) == 6
+    assert len(lines) == 8  # incl. two clouds with far outliers clamped into the border cells of a tight grid
     for ln in lines:
         assert "mismatching queries 0," in ln, ln
 

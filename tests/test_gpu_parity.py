@@ -500,6 +500,9 @@ def test_knn_grid_equals_brute_force(sx):
     dup = torch.randn(12_000, 3, generator=gen)
     dup[:3000] = dup[3000:6000]
     clouds["dup"] = dup
+    out = torch.randn(25_000, 3, generator=gen)
+    out[:40] *= 5000.0  # floaters far outside the robust grid box: clamped into border cells, still exact
+    clouds["outliers"] = out
     for name, c in clouds.items():
         c = c.to(DEV)
         a = sx.ops.knn_normals(c, 20, method="brute")
