@@ -81,9 +81,12 @@ class ShardedPoseEstimator:
         self.parts = getattr(self.backend, "parts", 1)
         if cache.scores is None:
             cache.scores = torch.empty(cache.n_rays, dtype=torch.float32, device=rays_ori.device)
-        # q_proj 1, (qprep + pass) x2 on the tensor-core path, merge 1, top-k 11 (+11 global), pose tail 1
+        # libsixdgs launches per query: pass 1 + merge + pass 2 (3, +2 q-prep on the tensor-core path), radix top-k
+        # (11; 1 when the shard has <= 4096 rays), pose tail 1, and when sharded candidate pack 1 + global top-k 1.
+        # The q projection is one launch per batch (launches_per_batch).
         tc = 2 if getattr(self.backend, "impl", 0) == ops.SCORE_TC else 0
-        self.launches_per_query = 1 + 2 + tc + 1 + 11 + 1 + (11 if world > 1 else 0)
+        self.launches_per_query = 3 + tc + (11 if cache.n_rays > 4096 else 1) + 1 + (2 if world > 1 else 0)
+        self.launches_per_batch = 1
         self._g = None  # captured graphs + static buffers
 
     # ------------------------------------------------------------------ collectives

@@ -435,7 +435,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if "bf16" in args.score_impl else "f32",
                 "data": "synthetic", "config": workload_config(args, n_total, n_local), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": est.launches_per_query * args.steps * B, "cuda_graph": bool(graph),
+                "gpu_launches": (est.launches_per_query * B + est.launches_per_batch) * args.steps, "cuda_graph": bool(graph),
                 "queries_per_step": B, "latency_b1": {"ms_per_query": lat_b1, "queries_per_s": (1e3 / lat_b1) if lat_b1 else None},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "prepare": {"scene_to_gpu_s": t1 - t0, "raygen_s": t2 - t1, "key_cache_s": t3 - t2,
