@@ -21,6 +21,7 @@ SOURCES = {
     "knn_grid.cu": ["-fmad=false"],
     "features.cu": [],
     "features_tc.cu": [],
+    "features_tc2.cu": [],
     "score_simt.cu": [],
     "score_tc.cu": [],
     "topk.cu": [],

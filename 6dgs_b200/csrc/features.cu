@@ -106,10 +106,16 @@ template <typename TO>
 int launch_linear_tc(const float* x, int64_t m, int k, int64_t lda, const float* w, const float* b, int n, TO* y,
                      int64_t ldc, int relu, int round_tf32, cudaStream_t s);
 
+// experimental CTA-pair, full-width-tile variant (features_tc2.cu)
+template <typename TO>
+int launch_linear_tc2(const float* x, int64_t m, int k, int64_t lda, const float* w, const float* b, int n, TO* y,
+                      int64_t ldc, int relu, int round_tf32, cudaStream_t s);
+
 // `feeds_gemm`: the output is the A operand of another tensor-core layer -> round it to TF32 on store
 template <typename TO>
 static int launch_any(int impl, const float* x, int64_t m, int k, int64_t lda, const float* w, const float* b, int n, TO* y,
                       int64_t ldc, int relu, cudaStream_t s, int feeds_gemm = 1) {
+  if (impl == 2) return launch_linear_tc2<TO>(x, m, k, lda, w, b, n, y, ldc, relu, feeds_gemm, s);
   return impl == 1 ? launch_linear_tc<TO>(x, m, k, lda, w, b, n, y, ldc, relu, feeds_gemm, s)
                    : launch_linear<TO>(x, m, k, lda, w, b, n, y, ldc, relu, s);
 }
@@ -142,7 +148,7 @@ extern "C" int sixdgs_ray_features(const float* ori, const float* dir, const flo
   SIXDGS_REQUIRE(!k_out || k_dtype == SIXDGS_F32 || k_dtype == SIXDGS_BF16, "unsupported k_dtype");
   SIXDGS_REQUIRE(!k_out || !wk || bk, "wk without bk");
   SIXDGS_REQUIRE(n >= 0, "negative size");
-  SIXDGS_REQUIRE(impl == 0 || impl == 1, "impl must be 0 (fp32 SIMT) or 1 (TF32 tcgen05)");
+  SIXDGS_REQUIRE(impl >= 0 && impl <= 2, "impl must be 0 (fp32 SIMT), 1 (TF32 tcgen05) or 2 (experimental CTA-pair TF32)");
   if (n == 0) return SIXDGS_OK;
   if (workspace == nullptr || workspace_bytes < sixdgs_ray_features_workspace(n)) {
     set_error("ray_features: workspace too small (%zu < %zu)", workspace_bytes, sixdgs_ray_features_workspace(n));
@@ -155,7 +161,7 @@ extern "C" int sixdgs_ray_features(const float* ori, const float* dir, const flo
   float* F = H + cap * 512;
   for (int64_t r0 = 0; r0 < n; r0 += cap) {
     const int64_t c = (n - r0) < cap ? (n - r0) : cap;
-    pe_kernel<<<(unsigned)((c + 127) / 128), 128, 0, s>>>(ori + r0 * 3, dir + r0 * 3, rgb + r0 * 3, c, X, impl == 1);
+    pe_kernel<<<(unsigned)((c + 127) / 128), 128, 0, s>>>(ori + r0 * 3, dir + r0 * 3, rgb + r0 * 3, c, X, impl >= 1);
     int rc = check_launch("pe");
     if (rc) return rc;
     // mlp.0: x(160) -> H(512), relu ; mlp.2: H -> X[:, :512], relu

@@ -101,7 +101,8 @@ int sixdgs_exclusive_scan(const int32_t* in, int64_t n, int64_t* out, void* stre
  *   w4 [384,512]  = mlp2.2.weight                     b4[384]
  *   wk [384,384]  = attention.k_proj.weight (nullable: skip projection, emit features) bk[384]
  * k_out[n,384] in k_dtype (SIXDGS_F32 | SIXDGS_BF16); feat_out (nullable) = pre-projection features.
- * impl: 0 = fp32 FMA GEMMs (exact path), 1 = TF32 tcgen05 GEMMs (TMA + TMEM; throughput path).
+ * impl: 0 = fp32 FMA GEMMs (exact path), 1 = TF32 tcgen05 GEMMs (TMA + TMEM; throughput path),
+ *       2 = experimental CTA-pair TF32 GEMMs with full-width tiles (opt-in).
  * workspace >= sixdgs_ray_features_workspace(n) bytes. */
 size_t sixdgs_ray_features_workspace(int64_t n);
 int sixdgs_ray_features(const float* ori, const float* dir, const float* rgb, int64_t n,
