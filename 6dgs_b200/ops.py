@@ -147,7 +147,8 @@ def pack_ray_mlp_weights(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch
 
 FEATURES_SIMT = 0  # fp32 FMA GEMMs (exact)
 FEATURES_TC = 1    # TF32 tcgen05 GEMMs
-FEATURES_TC2 = 2   # EXPERIMENTAL: CTA-pair full-width TF32 tiles (features_tc2.cu); opt-in, not validated yet
+FEATURES_TC2 = 2   # EXPERIMENTAL: CTA-pair full-width TF32 tiles (features_tc2.cu); correct, not faster (round 1)
+FEATURES_TC_STAGED = 3  # EXPERIMENTAL: 1-CTA kernel with a shared-memory staged TMA-store epilogue
 
 
 def ray_features(ori, dirs, rgb, pw: Dict[str, torch.Tensor], k_dtype: Optional[int] = F32, want_features: bool = False,
@@ -164,7 +165,7 @@ def ray_features(ori, dirs, rgb, pw: Dict[str, torch.Tensor], k_dtype: Optional[
         return k_out, feat
     wsz = int(_lib.load().sixdgs_ray_features_workspace(n))
     ws = torch.empty(wsz, dtype=torch.uint8, device=dev)
-    sfx = "_tf32" if impl in (FEATURES_TC, FEATURES_TC2) else ""
+    sfx = "_tf32" if impl in (FEATURES_TC, FEATURES_TC2, FEATURES_TC_STAGED) else ""
     call("sixdgs_ray_features", dptr(ori), dptr(dirs), dptr(rgb), n, dptr(pw["w1p" + sfx]), dptr(pw["b1"]),
          dptr(pw["w2" + sfx]), dptr(pw["b2"]), dptr(pw["w3p" + sfx]), dptr(pw["b3"]), dptr(pw["w4" + sfx]), dptr(pw["b4"]),
          dptr(pw["wk" + sfx]) if project else None, dptr(pw["bk"]) if project else None,

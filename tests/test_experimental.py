@@ -30,3 +30,22 @@ def test_cta_pair_tf32_gemm_matches_the_one_cta_kernel(sx, synthetic):
         assert (k2 - k0).abs().max().item() <= 1.5e-3 * scale, n
         kb, _ = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.BF16, impl=sx.ops.FEATURES_TC2)
         assert (kb.float() - k0).abs().max().item() <= 4e-3 * scale
+
+
+def test_staged_tma_store_epilogue_matches_the_direct_store_kernel(sx, synthetic):
+    """features_tc.cu: linear_tc_staged_kernel (smem-staged TMA tensor stores) must be bit-identical to
+    linear_tc_kernel (same MMAs, same epilogue math; only the way the tile reaches HBM differs)"""
+    dev = "cuda"
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone())
+    idm.load_state_dict(synthetic.synth_id_weights(seed=3), strict=False)
+    pw = idm.to(dev).packed_weights()
+    gen = torch.Generator().manual_seed(4)
+    for n in (1, 127, 128, 129, 200_000):
+        ori = (torch.randn(n, 3, generator=gen) * 3).to(dev)
+        dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1).to(dev)
+        rgb = torch.rand(n, 3, generator=gen).to(dev)
+        for kd in (sx._lib.F32, sx._lib.BF16):
+            k1, f1 = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=kd, want_features=True, impl=sx.ops.FEATURES_TC)
+            k3, f3 = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=kd, want_features=True, impl=sx.ops.FEATURES_TC_STAGED)
+            torch.cuda.synchronize()
+            assert torch.equal(k1, k3) and torch.equal(f1, f3), (n, kd)
