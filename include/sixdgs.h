@@ -3,7 +3,7 @@
  * pose-estimation hot path.
  *
  * The reference (mbortolon97/6dgs) has NO native boundary on this path -- it is pure torch ops in
- * pose_estimation/*.py -- so the entry points below are what a ctypes/pybind binding inside the
+ * the pose_estimation package -- so the entry points below are what a ctypes/pybind binding inside the
  * reference's Python functions would call.  The calling convention follows the
  * reference's only native precedent, free functions over raw device pointers
  * (submodules/simple-knn/simple_knn.h:18, spatial.cu:15-26).

@@ -128,3 +128,20 @@ def test_training_mode_refuses_cpu_tensors(sx, synthetic):
     r = torch.rand(10, 3)
     with pytest.raises(sx.SixdgsError, match="CUDA"):
         idm(img, mask, r, r, r)
+
+
+def test_header_is_valid_c_and_the_c_example_links(sx, tmp_path):
+    """include/sixdgs.h must be consumable from plain C (it is the drop-in boundary); the example links against the
+    in-tree .so and libcudart.  It is not run here (no GPU)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("gcc / CUDA headers not available")
+    sx._lib.load()
+    exe = str(tmp_path / "c_api_smoke")
+    csrc = os.path.join(ROOT, "6dgs_b200", "csrc")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                           os.path.join(ROOT, "examples", "c_api_smoke.c"), "-o", exe, "-L", csrc, "-lsixdgs",
+                           "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm", f"-Wl,-rpath,{csrc}"])
+    assert os.path.exists(exe)
