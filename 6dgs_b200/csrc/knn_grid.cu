@@ -5,7 +5,7 @@
 // query in cell order (neighbouring threads walk the same cells, so the point reads hit L1/L2).  The order of the
 // points inside a cell depends on atomics, the result does not: candidates are ranked by (distance, index), which
 // is independent of the order in which they are visited.  Points outside the grid box (the host may build it from
-// robust statistics so that a few far outliers do not inflate the cells) are clamped into the border cells; the
+// robust statistics (quantiles) so that a few far outliers do not inflate the cells) are clamped into the border cells; the
 // search treats faces on the grid boundary as open, so it stays exhaustive.
 #include "common.cuh"
 #include "normal_fit.cuh"

@@ -27,11 +27,18 @@ def degrade_mask(scaling_raw: torch.Tensor, target_points: int = 50) -> Tuple[to
 
 def _knn_grid_layout(c: torch.Tensor, points_per_cell: float = 8.0):
     """uniform grid over a robust box of the cloud: (lo[3], cell edge, dims[3]); one host read of the statistics.
-    The box is the bounding box clipped to mean +- 4 sigma per axis, so a few far outliers (floaters of a real 3DGS
-    scene) do not inflate the cells; points outside are clamped into border cells and the search stays exact."""
+    The box is the bounding box clipped to the 1 %..99 % quantile range (of a <= 65536-point strided subsample)
+    widened by half that range on each side, so a few far outliers (floaters of a real 3DGS scene) cannot inflate the
+    cells -- mean/sigma would not do: ten points at 1e6 drag sigma itself.  Points outside the box are clamped into
+    border cells and the search stays exact."""
     lo_t, hi_t = torch.aminmax(c, dim=0)
-    mu, sd = c.mean(dim=0), c.std(dim=0)
-    box = torch.stack((torch.maximum(lo_t, mu - 4 * sd), torch.minimum(hi_t, mu + 4 * sd))).cpu().double()
+    sub = c[:: max(1, c.shape[0] // 65536)]
+    k_lo = max(1, int(0.01 * sub.shape[0]))
+    k_hi = min(sub.shape[0], sub.shape[0] - k_lo + 1)
+    q_lo = torch.kthvalue(sub, k_lo, dim=0).values
+    q_hi = torch.kthvalue(sub, k_hi, dim=0).values
+    pad = 0.5 * (q_hi - q_lo)
+    box = torch.stack((torch.maximum(lo_t, q_lo - pad), torch.minimum(hi_t, q_hi + pad))).cpu().double()
     lo, hi = box[0], box[1]
     ext = (hi - lo).clamp_min(1e-12)
     m = c.shape[0]
