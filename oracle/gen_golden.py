@@ -107,6 +107,18 @@ def gen_rays():
     npz("rays_capped.npz", scene_n=1500, scene_seed=2, perm=perm2, n_rays=o2.shape[0],
         ori_s=o2[::16], dirs_s=d2[::16], rgb_s=c2[::16],
         sums=torch.stack((o2.double().sum(0), d2.double().sum(0), c2.double().sum(0))))
+    # heavy-tailed scales (log-normal, sigma 1.5): wide spread in cells per ellipsoid, some ellipsoids degraded
+    sc3 = synthetic.synth_scene(160, seed=21, heavy_tail=True)
+    sc3["scaling"] = -4.0 + 1.5 * torch.randn(160, 3, generator=torch.Generator().manual_seed(22))
+    gm3 = ref_model(sc3)
+    torch.manual_seed(79)
+    nvalid3 = int(ref_q.mask_degraded_ellipsoids(*torch.exp(sc3["scaling"]).unbind(-1)).sum())
+    perm3 = torch.randperm(nvalid3, dtype=torch.long)[: min(1000, nvalid3)]
+    torch.manual_seed(79)
+    o3, d3, c3 = ref_s.generate_all_possible_rays(gm3)
+    npz("rays_heavy.npz", scene_n=160, scene_seed=21, scaling=sc3["scaling"], n_valid=nvalid3, perm=perm3, n_rays=o3.shape[0],
+        ori_s=o3[::8], dirs_s=d3[::8], rgb_s=c3[::8],
+        sums=torch.stack((o3.double().sum(0), d3.double().sum(0), c3.double().sum(0))))
     return sc, ori, dirs, rgb
 
 
@@ -190,6 +202,9 @@ def gen_pose(idm, ori, dirs, rgb):
 
 
 if __name__ == "__main__":
+    if "--only-heavy" in sys.argv:  # add the heavy-tail fixture without touching the others
+        gen_rays()
+        sys.exit(0)
     gen_quadricell()
     gen_sym_eig()
     gen_normals()

@@ -65,6 +65,21 @@ def test_generate_rays_capped(oracle, synthetic):
     torch.testing.assert_close(rgb[::16], g["rgb_s"], rtol=0, atol=1e-7)
 
 
+def test_generate_rays_heavy_tail(oracle, synthetic):
+    """Log-normal scales: ~10x spread of cells per ellipsoid and a share of degraded (needle) ellipsoids."""
+    g = load_golden("rays_heavy.npz")
+    sc = synthetic.synth_scene(g["scene_n"], seed=g["scene_seed"], heavy_tail=True)
+    sc["scaling"] = g["scaling"]
+    assert int(g["n_valid"]) < int(g["scene_n"])  # the fixture does exercise the degrade mask
+    ori, dirs, rgb = oracle.generate_rays(sc["xyz"], sc["scaling"], sc["rotation"],
+                                          torch.cat((sc["features_dc"], sc["features_rest"]), 1),
+                                          ellipsoid_idx=g["perm"])
+    assert ori.shape[0] == g["n_rays"]
+    torch.testing.assert_close(ori[::8], g["ori_s"], rtol=0, atol=0)
+    torch.testing.assert_close(dirs[::8], g["dirs_s"], rtol=0, atol=0)
+    torch.testing.assert_close(rgb[::8], g["rgb_s"], rtol=0, atol=1e-7)
+
+
 def test_ray_features_and_scores(oracle, synthetic):
     g = load_golden("id_module.npz")
     r = load_golden("rays_small.npz")
