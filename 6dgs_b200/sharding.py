@@ -71,13 +71,24 @@ class ShardedPoseEstimator:
     ``query`` launches eagerly.  ``enable_cuda_graphs`` captures the pipeline with static buffers: a single
     graph on one GPU; on several GPUs three graph segments with the two NCCL all-gathers issued eagerly
     between them (a collective inside a captured graph ties the graph to NCCL's internal state and proved
-    fragile; two eager launches per query cost ~10 us)."""
+    fragile; two eager launches per query cost ~10 us).
+
+    ``front_end``: what the ranks do with the image front end (resize, backbone, q projection, up head) of a
+    batch.  "replicated" (default): every rank runs it for the whole batch -- no extra collective, but the
+    replicated milliseconds do not shrink with the world size.  "sharded": when the batch size is a multiple of
+    the world size each rank runs it for its B/world images only and one more all-gather (q rows, up vector and
+    token validity, ~394 KB per query) hands every rank the whole batch; other batch sizes fall back to
+    "replicated".  With ``query_batch(..., local=True)`` the caller passes just this rank's images, so only
+    those cross PCIe."""
 
     def __init__(self, idm, rays_ori: torch.Tensor, rays_dir: torch.Tensor, cache, rank: int = 0, world: int = 1,
-                 backend=None, group=None):
+                 backend=None, group=None, front_end: str = "replicated"):
+        if front_end not in ("replicated", "sharded"):
+            raise ValueError(f"front_end must be 'replicated' or 'sharded', got {front_end!r}")
         self.backend = backend or CudaBackend(idm)
         self.ori, self.dirs, self.cache = rays_ori, rays_dir, cache
         self.rank, self.world, self.group = rank, world, group
+        self.front_end = front_end
         self.parts = getattr(self.backend, "parts", 1)
         if cache.scores is None:
             cache.scores = torch.empty(cache.n_rays, dtype=torch.float32, device=rays_ori.device)
@@ -111,17 +122,64 @@ class ShardedPoseEstimator:
     # Every stage works on a BATCH of B queries: the image front end (resize, backbone, q projection, up head)
     # runs once for the batch -- it is latency-bound, so B images cost about as much as one -- while the key
     # cache is streamed per query (two passes each).  The collectives are per batch as well.
-    def _stage1(self, imgs, masks):
-        """images -> tokens -> q, camera up, and this shard's partial softmax rows for every query of the batch"""
+    def _front(self, imgs, masks):
+        """images -> tokens -> (q [B,n_img,384], unit up vectors [>=B,3], token validity [B,n_img] uint8 or None)"""
         b = self.backend
         tok_pe, grid, valid = b.tokens(imgs, masks)
         nb, n_img = tok_pe.shape[0], tok_pe.shape[1]
         q = b.project(tok_pe.reshape(nb * n_img, -1)).reshape(nb, n_img, -1)
+        return q, b.camera_up(grid), valid
+
+    def _pass1_all(self, q, up, valid):
+        """this shard's partial softmax rows for every query of the batch"""
+        b = self.backend
+        nb, n_img = q.shape[0], q.shape[1]
         parts = [b.pass1(self.cache.keys, q[i]) for i in range(nb)]
         pm = torch.cat([p[0] for p in parts], 0)  # [B * parts, 256]
         pz = torch.cat([p[1] for p in parts], 0)
-        return {"q": q, "valid": valid, "up": b.camera_up(grid), "pm": pm, "pz": pz, "n_img": n_img, "nb": nb,
+        return {"q": q, "valid": valid, "up": up, "pm": pm, "pz": pz, "n_img": n_img, "nb": nb,
                 "rows": parts[0][0].shape[0]}
+
+    def _stage1(self, imgs, masks):
+        """images -> tokens -> q, camera up, and this shard's partial softmax rows for every query of the batch"""
+        return self._pass1_all(*self._front(imgs, masks))
+
+    # ---- sharded front end: each rank's (q, up, valid) rows travel as one fp32 record per query, padded to a
+    # multiple of 64 floats so that every q block of the gathered buffer stays 256-byte aligned for the kernels
+    @staticmethod
+    def _record_len(n_img, d):
+        return -(-(n_img * d + 3 + n_img) // 64) * 64
+
+    def _pack_front(self, q, up, valid):
+        bl, n_img, d = q.shape
+        rec = torch.zeros((bl, self._record_len(n_img, d)), dtype=torch.float32, device=q.device)
+        rec[:, :n_img * d] = q.reshape(bl, -1)
+        rec[:, n_img * d:n_img * d + 3] = up[:bl]
+        if valid is None:
+            rec[:, n_img * d + 3:n_img * d + 3 + n_img] = 1.0
+        else:
+            rec[:, n_img * d + 3:n_img * d + 3 + n_img] = valid.to(torch.float32)
+        return rec
+
+    @staticmethod
+    def _unpack_front(rec, n_img, d):
+        q = rec[:, :n_img * d].unflatten(1, (n_img, d))  # a view: q[i] is contiguous and aligned
+        up = rec[:, n_img * d:n_img * d + 3]
+        valid = rec[:, n_img * d + 3:n_img * d + 3 + n_img].to(torch.uint8)
+        return q, up, valid
+
+    def _shards_front(self, n_batch: int, local: bool) -> bool:
+        if local:
+            if self.front_end != "sharded" or self.world == 1:
+                raise ValueError("local=True needs front_end='sharded' and more than one rank")
+            return True
+        return self.front_end == "sharded" and self.world > 1 and n_batch % self.world == 0
+
+    def _local_chunk(self, imgs, masks, local):
+        if local:
+            return imgs, masks
+        bl = imgs.shape[0] // self.world
+        return imgs[self.rank * bl:(self.rank + 1) * bl], masks[self.rank * bl:(self.rank + 1) * bl]
 
     def _stage2(self, pm, pz, st, k):
         """merged statistics -> scores -> local top-k per query (+ packed candidates when sharded).
@@ -158,8 +216,13 @@ class ShardedPoseEstimator:
             outs.append(b.pose_tail_candidates(c, gidx, gvals, up[i]))
         return torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
 
-    def _query_eager(self, imgs, masks, k):
-        st = self._stage1(imgs, masks)
+    def _query_eager(self, imgs, masks, k, local=False):
+        if self._shards_front(imgs.shape[0], local):
+            q, up, valid = self._front(*self._local_chunk(imgs, masks, local))
+            rec = self._all_gather(self._pack_front(q, up, valid))
+            st = self._pass1_all(*self._unpack_front(rec, q.shape[1], q.shape[2]))
+        else:
+            st = self._stage1(imgs, masks)
         pm, pz = st["pm"], st["pz"]
         if self.world > 1:
             pm, pz = self._all_gather(pm), self._all_gather(pz)
@@ -170,19 +233,23 @@ class ShardedPoseEstimator:
         return self._stage3(self._all_gather(cand), st["up"], k, st["nb"])
 
     # ------------------------------------------------------------------ CUDA graphs
-    def enable_cuda_graphs(self, img: torch.Tensor, mask: torch.Tensor, k: int = 100) -> bool:
+    def enable_cuda_graphs(self, img: torch.Tensor, mask: torch.Tensor, k: int = 100, local: bool = False) -> bool:
         """Capture the pipeline for image batches of this shape ([B,H,W,3] / [B,H,W]; a single [H,W,3] image is
-        treated as B = 1).  Returns False (and stays eager) if capture fails."""
+        treated as B = 1; ``local`` as in ``query_batch``).  Returns False (and stays eager) if capture fails."""
         if img.dim() == 3:
             img, mask = img[None], mask[None]
         cur = torch.cuda.current_stream()
-        g = {"img": img.clone(), "mask": mask.clone(), "k": k}
+        shard_front = self._shards_front(img.shape[0], local)
+        g = {"shape": tuple(img.shape), "local": local, "k": k}
+        if shard_front:  # the static input is this rank's chunk only
+            img, mask = self._local_chunk(img, mask, local)
+        g["img"], g["mask"] = img.clone(), mask.clone()
         try:
             side = torch.cuda.Stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    self._query_eager(g["img"], g["mask"], k)
+                    self._query_eager(g["img"], g["mask"], k, local=shard_front)
             cur.wait_stream(side)
             torch.cuda.synchronize()
             if self.world == 1:
@@ -192,8 +259,18 @@ class ShardedPoseEstimator:
                 g["graphs"] = [g1]
             else:
                 g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1):
-                    g["st"] = self._stage1(g["img"], g["mask"])
+                if shard_front:
+                    g0 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g0):
+                        q, up, valid = self._front(g["img"], g["mask"])
+                        g["rec"] = self._pack_front(q, up, valid)
+                    g["rec_all"] = self._all_gather(g["rec"])
+                    g["front_graph"] = g0
+                    with torch.cuda.graph(g1):
+                        g["st"] = self._pass1_all(*self._unpack_front(g["rec_all"], q.shape[1], q.shape[2]))
+                else:
+                    with torch.cuda.graph(g1):
+                        g["st"] = self._stage1(g["img"], g["mask"])
                 g["pm_all"] = self._all_gather(g["st"]["pm"])
                 g["pz_all"] = self._all_gather(g["st"]["pz"])
                 with torch.cuda.graph(g2):
@@ -214,6 +291,8 @@ class ShardedPoseEstimator:
 
     def _query_graphs(self, img, mask):
         g = self._g
+        if "front_graph" in g and not g["local"]:
+            img, mask = self._local_chunk(img, mask, False)
         if img.data_ptr() != g["img"].data_ptr():
             g["img"].copy_(img)
         if mask.data_ptr() != g["mask"].data_ptr():
@@ -221,6 +300,9 @@ class ShardedPoseEstimator:
         if self.world == 1:
             g["graphs"][0].replay()
         else:
+            if "front_graph" in g:
+                g["front_graph"].replay()
+                self._all_gather(g["rec"], g["rec_all"])
             g["graphs"][0].replay()
             self._all_gather(g["st"]["pm"], g["pm_all"])
             self._all_gather(g["st"]["pz"], g["pz_all"])
@@ -230,13 +312,15 @@ class ShardedPoseEstimator:
         return g["out"]
 
     @torch.no_grad()
-    def query_batch(self, imgs: torch.Tensor, masks: torch.Tensor, k: int = 100):
+    def query_batch(self, imgs: torch.Tensor, masks: torch.Tensor, k: int = 100, local: bool = False):
         """imgs [B,H,W,3], masks [B,H,W] -> (c2w[B,4,4], aux[B,8]); identical on every rank.  With graphs enabled
-        (for this batch shape) the returned tensors are the graph's static outputs, overwritten by the next call."""
+        (for this batch shape) the returned tensors are the graph's static outputs, overwritten by the next call.
+        ``local=True`` (front_end="sharded" only): imgs/masks hold just this rank's B/world images, in rank order;
+        the result still covers the whole batch."""
         g = self._g
-        if g is not None and g["k"] == k and imgs.shape == g["img"].shape and masks.shape == g["mask"].shape:
+        if g is not None and g["k"] == k and tuple(imgs.shape) == g["shape"] and local == g["local"]:
             return self._query_graphs(imgs, masks)
-        return self._query_eager(imgs, masks, k)
+        return self._query_eager(imgs, masks, k, local)
 
     @torch.no_grad()
     def query(self, img: torch.Tensor, mask: torch.Tensor, k: int = 100):

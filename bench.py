@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--cpu-sample-ellipsoids", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--front-end", choices=("replicated", "sharded"), default="replicated",
+                    help="N>1: every rank runs the image front end for the whole batch, or only for its B/N images "
+                         "(one more all-gather per batch; the e2e leg then uploads each image once)")
     ap.add_argument("--batch", type=int, default=8,
                     help="queries per step: the image front end (resize, backbone, q projection, up head) runs once per "
                          "batch, the key cache is streamed per query; 1 = one query per step")
@@ -237,6 +240,7 @@ def workload_config(args, n_rays, n_rays_local):
                         f"image, {args.score_impl} key cache, fp32 LS solve (BASELINE.json configs[2])",
             "gaussians": args.gaussians, "n_rays": n_rays, "n_rays_per_rank": n_rays_local, "image": [args.height, args.width],
             "n_img_tokens": 256, "queries_per_step": args.batch, "score_impl": args.score_impl, "backbone": args.backbone, "backbone_matmul": args.backbone_matmul,
+            "front_end": args.front_end if args.gpus > 1 else "single",
             "parallelism": f"ray-shard x{args.gpus}", "l2": "inputs larger than L2 (key cache >> 126 MB), no flush needed"}
 
 
@@ -288,7 +292,7 @@ def main():
         t = torch.tensor([n_local], device=dev, dtype=torch.long)
         dist.all_reduce(t)
         n_total = int(t.item())
-    est = sharding.ShardedPoseEstimator(idm, ori, dirs, cache, rank, world)
+    est = sharding.ShardedPoseEstimator(idm, ori, dirs, cache, rank, world, front_end=args.front_end)
 
     B = args.batch
     img_u8 = torch.stack([(sx.synthetic.synth_image(args.height, args.width, seed=7 + i) * 255).to(torch.uint8) for i in range(B)])
@@ -296,8 +300,13 @@ def main():
     img_dev = (img_u8.to(dev).float() / 255.0).contiguous()
     mask_dev = torch.ones(B, args.height, args.width, dtype=torch.bool, device=dev)
 
+    # front_end="sharded": every rank holds (and, in the e2e leg, uploads) only its own B/world images
+    local = args.front_end == "sharded" and world > 1 and B % world == 0
+    lo, hi = (rank * (B // world), (rank + 1) * (B // world)) if local else (0, B)
+    img_q, mask_q = img_dev[lo:hi], mask_dev[lo:hi]
+
     def query():
-        return est.query_batch(img_dev, mask_dev)
+        return est.query_batch(img_q, mask_q, local=local)
 
     # one-query-per-step latency figure (eager + its own graphs), measured before the batched graphs are captured
     lat_b1 = None
@@ -325,9 +334,9 @@ def main():
     burst1, burst2 = time_score_kernels(sx, idm, cache, dev, 2, 4)
     graph = False
     if not args.no_graph:
-        graph = est.enable_cuda_graphs(img_dev, mask_dev)
+        graph = est.enable_cuda_graphs(img_q, mask_q, local=local)
         if graph:
-            g_out = est.query_batch(img_dev, mask_dev)
+            g_out = query()
             torch.cuda.synchronize()
             if not torch.allclose(g_out[0], c2w, atol=1e-5, equal_nan=True):
                 print("[bench] CUDA graph replay does not reproduce the eager pose; timing eager launches", file=sys.stderr)
@@ -367,13 +376,14 @@ def main():
     # ---------------- e2e: host image -> pose on host, through the public API ----------------
     pose_host = torch.empty(B, 4, 4).pin_memory()
 
-    img_e2e = torch.empty_like(img_dev)
+    img_e2e = torch.empty_like(img_q)
+    img_host_q = img_host[lo:hi]
 
     def e2e_step():
-        d = img_host.to(dev, non_blocking=True)
+        d = img_host_q.to(dev, non_blocking=True)
         torch.div(d, 255.0, out=img_e2e)  # uint8 -> [0,1] float (test.py:69-73)
         m = torch.ones_like(img_e2e[..., 0], dtype=torch.bool)
-        c, _ = est.query_batch(img_e2e, m)
+        c, _ = est.query_batch(img_e2e, m, local=local)
         pose_host.copy_(c, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 

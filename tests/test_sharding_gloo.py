@@ -27,11 +27,14 @@ class OracleBackend:
 
     def __init__(self, oracle, weights, tok_pe, up):
         self.o, self.w, self.tok_pe, self.up = oracle, weights, tok_pe, up
+        self.front_batches = []  # how many images each front-end call saw
 
     def tokens(self, imgs, masks):
-        # query i of the batch sees the fixture tokens scaled by (1 + 0.05 i): distinct queries, same rays
+        # an image filled with the value i sees the fixture tokens scaled by (1 + 0.05 i): distinct queries, same
+        # rays, and the tokens depend on the image content only (not on its position in whatever batch a rank holds)
         nb = imgs.shape[0]
-        return torch.stack([self.tok_pe * (1.0 + 0.05 * i) for i in range(nb)]), None, None
+        self.front_batches.append(nb)
+        return torch.stack([self.tok_pe * (1.0 + 0.05 * float(imgs[i].mean())) for i in range(nb)]), None, None
 
     def project(self, tok_pe):
         return torch.nn.functional.linear(tok_pe, self.w["attention.q_proj.weight"], self.w["attention.q_proj.bias"])
@@ -77,7 +80,7 @@ class OracleBackend:
         return c2w, torch.zeros(8)
 
 
-def _worker(rank, world, port, out_path, nb=1):
+def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -97,8 +100,16 @@ def _worker(rank, world, port, out_path, nb=1):
                                       w["attention.k_proj.weight"], w["attention.k_proj.bias"])
     cache = sx.RayKeyCache(keys, hi - lo, ())
     be = OracleBackend(oracle, w, g["tok_pe"], g["up"])
-    est = sx.ShardedPoseEstimator(None, ori[lo:hi].contiguous(), dirs[lo:hi].contiguous(), cache, rank, world, backend=be)
-    c2w, _ = est.query_batch(torch.zeros(nb, 2, 2, 3), torch.ones(nb, 2, 2, dtype=torch.bool), k=100)
+    est = sx.ShardedPoseEstimator(None, ori[lo:hi].contiguous(), dirs[lo:hi].contiguous(), cache, rank, world, backend=be,
+                                  front_end=front_end)
+    imgs = torch.arange(nb, dtype=torch.float32)[:, None, None, None].expand(nb, 2, 2, 3).contiguous()
+    masks = torch.ones(nb, 2, 2, dtype=torch.bool)
+    if local:  # hand over this rank's images only
+        bl = nb // world
+        imgs, masks = imgs[rank * bl:(rank + 1) * bl], masks[rank * bl:(rank + 1) * bl]
+    c2w, _ = est.query_batch(imgs, masks, k=100, local=local)
+    shards = front_end == "sharded" and nb % world == 0
+    assert be.front_batches == [nb // world if shards else nb]  # the front end ran once, on this rank's share
     # every rank must hold the same poses
     gathered = [torch.empty_like(c2w) for _ in range(world)]
     dist.all_gather(gathered, c2w)
@@ -108,20 +119,24 @@ def _worker(rank, world, port, out_path, nb=1):
     dist.destroy_process_group()
 
 
+# replicated front end, batch 3; sharded front end with an odd batch (falls back to replicated), with an even batch
+# given whole, and with each rank given only its own images
 @pytest.mark.timeout(300)
-def test_two_rank_sharded_query_matches_single_process(oracle, synthetic, tmp_path):
+@pytest.mark.parametrize("nb,front_end,local", [(3, "replicated", False), (3, "sharded", False),
+                                                (4, "sharded", False), (4, "sharded", True)])
+def test_two_rank_sharded_query_matches_single_process(oracle, synthetic, tmp_path, nb, front_end, local):
     from conftest import load_golden
     out = str(tmp_path / "c2w.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out, 3), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, nb, front_end, local), nprocs=2, join=True)
     c2w = torch.load(out)
-    assert c2w.shape == (3, 4, 4)
+    assert c2w.shape == (nb, 4, 4)
     g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
     ref, _ = oracle.pose_tail(g["topk_idx"], g["topk_vals"], r["ori"], r["dirs"], g["up"])
     torch.testing.assert_close(c2w[0], ref, rtol=1e-5, atol=1e-5)
     # the other queries of the batch (scaled tokens) against the unsharded oracle
     w = synthetic.synth_id_weights(seed=g["weight_seed"])
     fea = oracle.ray_features(r["ori"], r["dirs"], r["rgb"], w)
-    for i in (1, 2):
+    for i in range(1, nb):
         score, _ = oracle.attention_scores(g["tok_pe"] * (1.0 + 0.05 * i), fea, w, return_map=False)
         top = torch.topk(score, 100)
         ref_i, _ = oracle.pose_tail(top.indices, top.values, r["ori"], r["dirs"], g["up"])
@@ -138,5 +153,9 @@ def test_single_rank_path_uses_no_collective(sx, oracle, synthetic):
     est = sx.ShardedPoseEstimator(None, r["ori"], r["dirs"], sx.RayKeyCache(keys, keys.shape[0], ()), 0, 1,
                                   backend=OracleBackend(oracle, w, g["tok_pe"], g["up"]))
     c2w, _ = est.query(torch.zeros(2, 2, 3), torch.ones(2, 2, dtype=torch.bool))
+    with pytest.raises(ValueError):  # nothing to shard the front end over
+        est.query_batch(torch.zeros(1, 2, 2, 3), torch.ones(1, 2, 2, dtype=torch.bool), local=True)
+    with pytest.raises(ValueError):
+        sx.ShardedPoseEstimator(None, r["ori"], r["dirs"], est.cache, 0, 1, backend=est.backend, front_end="rank0")
     ref, _ = oracle.pose_tail(g["topk_idx"], g["topk_vals"], r["ori"], r["dirs"], g["up"])
     torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
