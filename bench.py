@@ -13,8 +13,8 @@ QUERIES per second; `latency_b1` in the same line is the one-query-per-step figu
 (ray generation + key cache) is per scene, not per query, and is reported separately.
 
   value     queries/s, image already resident in HBM, whole query captured in one CUDA graph
-  e2e       queries/s through IdentificationModule.query_pose() from a pinned uint8 HOST image
-            (H2D + /255 + mask inside the timed region) to the 4x4 pose back on the host
+  e2e       queries/s through ShardedPoseEstimator.query_batch() from pinned uint8 HOST images
+            (H2D + /255 + mask inside the timed region) to the 4x4 poses back on the host
   roofline  ray-score kernels (score_tc pass 1 / pass 2), algorithmic bytes / CUDA-event time / measured HBM peak
   cpu_baseline  the oracle port (torch CPU, all host threads) on a bounded sample of the same rays,
             extrapolated linearly in the ray count (per-ray work is independent; stated in `sample`)
