@@ -49,3 +49,45 @@ def test_staged_tma_store_epilogue_matches_the_direct_store_kernel(sx, synthetic
             k3, f3 = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=kd, want_features=True, impl=sx.ops.FEATURES_TC_STAGED)
             torch.cuda.synchronize()
             assert torch.equal(k1, k3) and torch.equal(f1, f3), (n, kd)
+
+
+def test_sharded_front_end_two_shards_in_one_process(sx, synthetic, oracle):
+    """ShardedPoseEstimator(front_end="sharded") on the CUDA backend: each of two shards runs the image front end
+    for ONE of the two images, the all-gather of the packed (q, up, validity) records is emulated by concatenation
+    in rank order, and the rest of the pipeline must reproduce the unsharded poses (the host logic alone is
+    covered on CPU by tests/test_sharding_gloo.py)."""
+    from conftest import load_golden
+    dev = "cuda"
+    g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
+    ori, dirs, rgb = r["ori"].to(dev), r["dirs"].to(dev), r["rgb"].to(dev)
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone(), score_impl="simt_fp32")
+    idm.load_state_dict(synthetic.synth_id_weights(seed=g["weight_seed"]), strict=False)
+    idm = idm.to(dev).eval().requires_grad_(False)
+    img = g["img"].to(dev)
+    imgs = torch.stack((img, img.flip(1)))
+    masks = torch.stack((torch.ones(64, 64, dtype=torch.bool, device=dev), g["mask2"].to(dev)))
+    full = sx.ShardedPoseEstimator(idm, ori, dirs, idm.build_key_cache(ori, dirs, rgb))
+    ref, _ = full.query_batch(imgs, masks)
+    n = ori.shape[0]
+    cut = n // 2 + 37
+    shards = []
+    for rank, (lo, hi) in enumerate(((0, cut), (cut, n))):
+        o, d, c = ori[lo:hi].contiguous(), dirs[lo:hi].contiguous(), rgb[lo:hi].contiguous()
+        shards.append(sx.ShardedPoseEstimator(idm, o, d, idm.build_key_cache(o, d, c), rank, 2, front_end="sharded"))
+    recs = []
+    for s in shards:
+        assert s._shards_front(2, False)
+        q, up, valid = s._front(*s._local_chunk(imgs, masks, False))
+        assert q.shape[0] == 1
+        recs.append(s._pack_front(q, up, valid))
+    rec = torch.cat(recs)
+    assert rec.shape[1] % 64 == 0
+    k = 100
+    sts = [s._pass1_all(*s._unpack_front(rec, 256, 384)) for s in shards]
+    assert all(st["q"][i].is_contiguous() and st["q"][i].data_ptr() % 256 == 0 for st in sts for i in range(2))
+    pm = torch.cat([st["pm"] for st in sts])
+    pz = torch.cat([st["pz"] for st in sts])
+    allc = torch.cat([s._stage2(pm, pz, st, k)[2] for s, st in zip(shards, sts)])
+    for s, st in zip(shards, sts):
+        c2w, _ = s._stage3(allc, st["up"], k, st["nb"])
+        torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
