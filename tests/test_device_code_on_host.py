@@ -2,6 +2,8 @@
 compiled with g++ and run here, so the discrete logic is verified without a GPU.
   * knn_grid.cuh -- the exhaustive uniform-grid k-NN search against brute force (must match exactly, ties included)
   * eig3.cuh     -- the closed-form 3x3 eigen-solver against the reference fixture
+  * normal_fit.cuh -- neighbourhood -> normal (scatter matrix, smallest eigenvector, majority-sign flip) against the
+                    reference's compute_normals fixture
 """
 import ctypes
 import os
@@ -45,3 +47,20 @@ def test_eig3_device_code_vs_reference_fixture(tmp_path):
     gap = (torch.minimum(g["vals"][:, 1] - g["vals"][:, 0], g["vals"][:, 2] - g["vals"][:, 1]).numpy() / scale) > 1e-2
     dots = (vecs * g["vecs"].numpy()).sum(1)
     assert (dots[gap] > 0.9999).all()
+
+
+def test_normal_fit_device_code_vs_reference_fixture(tmp_path):
+    so = str(tmp_path / "normal_host.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", CSRC, "-o", so,
+                           os.path.join(ROOT, "tests", "host", "normal_fit_host.cpp")])
+    lib = ctypes.CDLL(so)
+    g = load_golden("normals.npz")
+    cloud = np.ascontiguousarray(g["cloud"].numpy())
+    ref = g["normals"].numpy()
+    nq = ref.shape[0]
+    out = np.zeros((nq, 3), np.float32)
+    lib.host_knn_normals(cloud.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(cloud.shape[0]), ctypes.c_int64(nq),
+                         ctypes.c_int(20), out.ctypes.data_as(ctypes.c_void_p))
+    assert np.allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-5)
+    dots = (out * ref).sum(1)
+    assert (dots > 1 - 1e-5).all(), float(dots.min())  # direction and sign (majority vote) of every normal
