@@ -53,7 +53,8 @@ def parse():
     ap.add_argument("--backbone-matmul", default="tf32", choices=["fp32", "tf32"],
                     help="precision of the torch matmuls inside the ViT backbone / camera-up head (boundary "
                          "components, PyTorch): tf32 = torch.set_float32_matmul_precision('high')")
-    ap.add_argument("--cpu-sample-ellipsoids", type=int, default=4000)
+    ap.add_argument("--cpu-sample-ellipsoids", type=int, default=16000,
+                    help="CPU arm: ellipsoids whose rays (x29) are timed, 16 reference-sized chunks of 29k rays; ~10-20 s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--front-end", choices=("replicated", "sharded"), default="replicated",
