@@ -45,6 +45,11 @@ _SIGNATURES = {
     "sixdgs_score_pass1": ([c_p, c_i, c_i64, c_p, c_i, c_p, c_p, c_i, c_p, c_sz, c_p], c_i),
     "sixdgs_score_merge": ([c_p, c_p, c_i, c_i, c_i64, c_i, c_p, c_p, c_p, c_p], c_i),
     "sixdgs_score_pass2": ([c_p, c_i, c_i64, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_sz, c_p], c_i),
+    "sixdgs_score_batch_max": ([], c_i),
+    "sixdgs_score_batch_parts": ([], c_i),
+    "sixdgs_score_batch_workspace": ([c_i], c_sz),
+    "sixdgs_score_pass1_batch": ([c_p, c_i, c_i64, c_p, c_i, c_i, c_p, c_p, c_p, c_sz, c_p], c_i),
+    "sixdgs_score_pass2_batch": ([c_p, c_i, c_i64, c_p, c_i, c_i, c_p, c_p, c_p, c_i64, c_p, c_sz, c_p], c_i),
     "sixdgs_topk_workspace": ([c_i64, c_i], c_sz),
     "sixdgs_topk": ([c_p, c_i64, c_i, c_p, c_p, c_p, c_sz, c_p], c_i),
     "sixdgs_line_intersect": ([c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p], c_i),

@@ -24,6 +24,7 @@ SOURCES = {
     "features_tc2.cu": [],
     "score_simt.cu": [],
     "score_tc.cu": [],
+    "score_tc_mq.cu": [],
     "topk.cu": [],
     "pose.cu": ["-fmad=false"],
 }

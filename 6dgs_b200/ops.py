@@ -252,6 +252,55 @@ def score_pass2(k_cache: torch.Tensor, q: torch.Tensor, m: torch.Tensor, z: torc
     return scores, amap
 
 
+# ---- several queries per key sweep (EXPERIMENTAL, csrc/score_tc_mq.cu) ---------------------------------------
+def score_batch_max() -> int:
+    return int(_lib.load().sixdgs_score_batch_max())
+
+
+def _score_batch_workspace(device) -> torch.Tensor:
+    key = ("mq", str(device), stream_ptr())
+    if key not in _score_ws:
+        n = int(_lib.load().sixdgs_score_batch_workspace(score_batch_max()))
+        _score_ws[key] = torch.empty(n, dtype=torch.uint8, device=device)
+    return _score_ws[key]
+
+
+def _check_batch_q(q: torch.Tensor):
+    if q.dim() != 3 or q.shape[1] != MAX_TOKENS or q.shape[2] != FEAT:
+        raise _lib.SixdgsError(f"batched scoring needs q [B, {MAX_TOKENS}, {FEAT}], got {tuple(q.shape)}")
+
+
+def score_pass1_batch(k_cache: torch.Tensor, q: torch.Tensor, n_img: int = MAX_TOKENS):
+    """q [B,256,384] -> partial rows pm, pz [B * parts, 256] (query-major, the layout of B score_pass1 calls)"""
+    _check_batch_q(q)
+    lib = _lib.load()
+    nb, parts, step = q.shape[0], int(lib.sixdgs_score_batch_parts()), score_batch_max()
+    ws = _score_batch_workspace(q.device)
+    pm = torch.empty(nb * parts, MAX_TOKENS, dtype=torch.float32, device=q.device)
+    pz = torch.empty(nb * parts, MAX_TOKENS, dtype=torch.float32, device=q.device)
+    for b0 in range(0, nb, step):
+        nq = min(step, nb - b0)
+        call("sixdgs_score_pass1_batch", dptr(k_cache, None), _kdtype(k_cache), k_cache.shape[0], dptr(q[b0:b0 + nq]), nq,
+             n_img, dptr(pm[b0 * parts:(b0 + nq) * parts]), dptr(pz[b0 * parts:(b0 + nq) * parts]), dptr(ws, torch.uint8),
+             ws.numel(), stream_ptr())
+    return pm, pz
+
+
+def score_pass2_batch(k_cache: torch.Tensor, q: torch.Tensor, m: torch.Tensor, z: torch.Tensor, n_img: int = MAX_TOKENS,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B,256,384], m / z [B,256] -> scores [B, n_rays]"""
+    _check_batch_q(q)
+    nb, n, step = q.shape[0], k_cache.shape[0], score_batch_max()
+    scores = out if out is not None else torch.empty(nb, n, dtype=torch.float32, device=q.device)
+    ws = _score_batch_workspace(q.device)
+    for b0 in range(0, nb, step):
+        nq = min(step, nb - b0)
+        call("sixdgs_score_pass2_batch", dptr(k_cache, None), _kdtype(k_cache), n, dptr(q[b0:b0 + nq]), nq, n_img,
+             dptr(m[b0:b0 + nq]), dptr(z[b0:b0 + nq]), dptr(scores[b0:b0 + nq]), scores.stride(0), dptr(ws, torch.uint8),
+             ws.numel(), stream_ptr())
+    return scores
+
+
 def topk(scores: torch.Tensor, k: int):
     n = scores.shape[0]
     vals = torch.empty(k, dtype=torch.float32, device=scores.device)

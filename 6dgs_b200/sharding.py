@@ -54,6 +54,13 @@ class CudaBackend:
     def pass2(self, keys, q, m, z, out):
         return ops.score_pass2(keys, q, m, z, self.impl, out=out)[0]
 
+    # several queries per key sweep (EXPERIMENTAL; ShardedPoseEstimator(multi_query=True), bf16 key cache only)
+    def pass1_batch(self, keys, q):
+        return ops.score_pass1_batch(keys, q)
+
+    def pass2_batch(self, keys, q, m, z, out):
+        return ops.score_pass2_batch(keys, q, m, z, out=out)
+
     def topk(self, scores, k):
         return ops.topk(scores, k)
 
@@ -79,16 +86,23 @@ class ShardedPoseEstimator:
     the world size each rank runs it for its B/world images only and one more all-gather (q rows, up vector and
     token validity, ~394 KB per query) hands every rank the whole batch; other batch sizes fall back to
     "replicated".  With ``query_batch(..., local=True)`` the caller passes just this rank's images, so only
-    those cross PCIe."""
+    those cross PCIe.
+
+    ``multi_query`` (EXPERIMENTAL, tensor-core path only): score the whole batch in one sweep over the key cache per
+    pass (csrc/score_tc_mq.cu) instead of one sweep per query."""
 
     def __init__(self, idm, rays_ori: torch.Tensor, rays_dir: torch.Tensor, cache, rank: int = 0, world: int = 1,
-                 backend=None, group=None, front_end: str = "replicated"):
+                 backend=None, group=None, front_end: str = "replicated", multi_query: bool = False):
         if front_end not in ("replicated", "sharded"):
             raise ValueError(f"front_end must be 'replicated' or 'sharded', got {front_end!r}")
         self.backend = backend or CudaBackend(idm)
         self.ori, self.dirs, self.cache = rays_ori, rays_dir, cache
         self.rank, self.world, self.group = rank, world, group
         self.front_end = front_end
+        self.multi_query = bool(multi_query)
+        if self.multi_query and getattr(self.backend, "impl", ops.SCORE_TC) != ops.SCORE_TC:
+            raise ValueError("multi_query needs the tensor-core score path (score_impl='tc_bf16')")
+        self._scores_b = None  # [B, n_rays] score rows of a batch (multi_query)
         self.parts = getattr(self.backend, "parts", 1)
         if cache.scores is None:
             cache.scores = torch.empty(cache.n_rays, dtype=torch.float32, device=rays_ori.device)
@@ -98,6 +112,9 @@ class ShardedPoseEstimator:
         tc = 2 if getattr(self.backend, "impl", 0) == ops.SCORE_TC else 0
         self.launches_per_query = 3 + tc + (11 if cache.n_rays > 4096 else 1) + 1 + (2 if world > 1 else 0)
         self.launches_per_batch = 1
+        if self.multi_query:  # per query only the merge remains; per batch (of <= 8) q-prep + kernel for each pass
+            self.launches_per_query -= 2 + tc
+            self.launches_per_batch += 4
         self._g = None  # captured graphs + static buffers
 
     # ------------------------------------------------------------------ collectives
@@ -134,11 +151,16 @@ class ShardedPoseEstimator:
         """this shard's partial softmax rows for every query of the batch"""
         b = self.backend
         nb, n_img = q.shape[0], q.shape[1]
-        parts = [b.pass1(self.cache.keys, q[i]) for i in range(nb)]
-        pm = torch.cat([p[0] for p in parts], 0)  # [B * parts, 256]
-        pz = torch.cat([p[1] for p in parts], 0)
-        return {"q": q, "valid": valid, "up": up, "pm": pm, "pz": pz, "n_img": n_img, "nb": nb,
-                "rows": parts[0][0].shape[0]}
+        if self.multi_query:
+            q = q.contiguous()  # the batched kernel reads the batch as one [B*256, 384] matrix
+            pm, pz = b.pass1_batch(self.cache.keys, q)  # [B * parts, 256], query-major like the loop below
+            rows = pm.shape[0] // nb
+        else:
+            parts = [b.pass1(self.cache.keys, q[i]) for i in range(nb)]
+            pm = torch.cat([p[0] for p in parts], 0)  # [B * parts, 256]
+            pz = torch.cat([p[1] for p in parts], 0)
+            rows = parts[0][0].shape[0]
+        return {"q": q, "valid": valid, "up": up, "pm": pm, "pz": pz, "n_img": n_img, "nb": nb, "rows": rows}
 
     def _stage1(self, imgs, masks):
         """images -> tokens -> q, camera up, and this shard's partial softmax rows for every query of the batch"""
@@ -192,11 +214,24 @@ class ShardedPoseEstimator:
         cand = None
         if self.world > 1:
             cand = torch.empty((nb, k, 7), dtype=torch.float32, device=self.ori.device)
-        for i in range(nb):
+        def merged(i):
             # query i's rows: [rank g][query i][0..rows) -> group stride nb*rows, first row i*rows (no copies)
-            m, z = b.merge(pm, pz, st["n_img"], st["valid"][i] if st["valid"] is not None else None,
+            return b.merge(pm, pz, st["n_img"], st["valid"][i] if st["valid"] is not None else None,
                            rows=rows, groups=groups, group_stride=nb * rows, first_row=i * rows)
-            scores = b.pass2(self.cache.keys, st["q"][i], m, z, self.cache.scores)
+
+        scores_b = None
+        if self.multi_query:
+            mz = [merged(i) for i in range(nb)]
+            if self._scores_b is None or self._scores_b.shape[0] < nb:
+                self._scores_b = torch.empty((nb, self.cache.n_rays), dtype=torch.float32, device=self.ori.device)
+            scores_b = b.pass2_batch(self.cache.keys, st["q"], torch.stack([x[0] for x in mz]),
+                                     torch.stack([x[1] for x in mz]), self._scores_b[:nb])
+        for i in range(nb):
+            if scores_b is not None:
+                scores = scores_b[i]
+            else:
+                m, z = merged(i)
+                scores = b.pass2(self.cache.keys, st["q"][i], m, z, self.cache.scores)
             v, ix = b.topk(scores, k_local)
             vals.append(v)
             idxs.append(ix)

@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--front-end", choices=("replicated", "sharded"), default="replicated",
                     help="N>1: every rank runs the image front end for the whole batch, or only for its B/N images "
                          "(one more all-gather per batch; the e2e leg then uploads each image once)")
+    ap.add_argument("--multi-query", action="store_true",
+                    help="EXPERIMENTAL: score the whole batch in one sweep over the key cache per pass (score_tc_mq.cu)")
     ap.add_argument("--batch", type=int, default=8,
                     help="queries per step: the image front end (resize, backbone, q projection, up head) runs once per "
                          "batch, the key cache is streamed per query; 1 = one query per step")
@@ -242,6 +244,7 @@ def workload_config(args, n_rays, n_rays_local):
             "gaussians": args.gaussians, "n_rays": n_rays, "n_rays_per_rank": n_rays_local, "image": [args.height, args.width],
             "n_img_tokens": 256, "queries_per_step": args.batch, "score_impl": args.score_impl, "backbone": args.backbone, "backbone_matmul": args.backbone_matmul,
             "front_end": args.front_end if args.gpus > 1 else "single",
+            "score_sweeps": "per batch (multi-query kernel)" if args.multi_query else "per query",
             "parallelism": f"ray-shard x{args.gpus}", "l2": "inputs larger than L2 (key cache >> 126 MB), no flush needed"}
 
 
@@ -293,7 +296,8 @@ def main():
         t = torch.tensor([n_local], device=dev, dtype=torch.long)
         dist.all_reduce(t)
         n_total = int(t.item())
-    est = sharding.ShardedPoseEstimator(idm, ori, dirs, cache, rank, world, front_end=args.front_end)
+    est = sharding.ShardedPoseEstimator(idm, ori, dirs, cache, rank, world, front_end=args.front_end,
+                                        multi_query=args.multi_query)
 
     B = args.batch
     img_u8 = torch.stack([(sx.synthetic.synth_image(args.height, args.width, seed=7 + i) * 255).to(torch.uint8) for i in range(B)])

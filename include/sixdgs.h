@@ -140,6 +140,23 @@ int sixdgs_score_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const f
                        const float* m, const float* z, float* scores, float* attn_map, int impl,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a11, several queries per key sweep -------- our_multihead_attention.py:4-12,70-79;
+ *                                                  identification_module.py:80-82 (one call per image there)
+ * EXPERIMENTAL (not used by any default path yet).  Same mathematics as score_pass1 / score_pass2 with impl 1,
+ * for n_queries <= sixdgs_score_batch_max() queries that share the key cache: q[n_queries, 256, 384] fp32,
+ * part_m / part_z [n_queries, sixdgs_score_batch_parts(), 256], m / z [n_queries, 256],
+ * scores[n_queries, score_stride] (score_stride >= n_rays).  The keys cross HBM once per pass for the whole batch.
+ * bf16 key cache only; workspace >= sixdgs_score_batch_workspace(n_queries). */
+int sixdgs_score_batch_max(void);
+int sixdgs_score_batch_parts(void);
+size_t sixdgs_score_batch_workspace(int n_queries);
+int sixdgs_score_pass1_batch(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries,
+                             int n_img, float* part_m, float* part_z, void* workspace, size_t workspace_bytes,
+                             void* stream);
+int sixdgs_score_pass2_batch(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries,
+                             int n_img, const float* m, const float* z, float* scores, int64_t score_stride,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a12: top-k -------- identification_module.py:131 (torch.topk, sorted descending) -----------
  * workspace >= sixdgs_topk_workspace(n, k).  idx int64, ties broken by lower index first. */
 size_t sixdgs_topk_workspace(int64_t n, int k);

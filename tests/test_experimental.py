@@ -91,3 +91,56 @@ def test_sharded_front_end_two_shards_in_one_process(sx, synthetic, oracle):
     for s, st in zip(shards, sts):
         c2w, _ = s._stage3(allc, st["up"], k, st["nb"])
         torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("n_rays,n_img", [(1, 256), (100, 256), (5513, 201), (74 * 256 * 3 + 77, 256)])
+def test_multi_query_score_kernel_equals_per_query_kernel(sx, n_rays, n_img):
+    """score_tc_mq.cu (several queries per key sweep) against score_tc.cu (validated): same tiles per CTA pair, same
+    MMA order per accumulator, same epilogue arithmetic -> the partial softmax rows and the scores must be
+    bit-identical, for batch sizes below, at and above one launch's capacity."""
+    dev = "cuda"
+    gen = torch.Generator().manual_seed(n_rays)
+    keys = (torch.randn(n_rays, 384, generator=gen) * 0.7).to(dev).to(torch.bfloat16)
+    parts = int(sx._lib.load().sixdgs_score_batch_parts())
+    assert parts == int(sx._lib.load().sixdgs_score_parts(sx.ops.SCORE_TC))
+    for nb in (1, 3, sx.ops.score_batch_max(), sx.ops.score_batch_max() + 3):
+        q = (torch.randn(nb, 256, 384, generator=gen) * 1.5).to(dev)
+        pm_b, pz_b = sx.ops.score_pass1_batch(keys, q, n_img)
+        ms, zs = [], []
+        for i in range(nb):
+            pm, pz = sx.ops.score_pass1(keys, q[i, :n_img].contiguous(), sx.ops.SCORE_TC)
+            torch.cuda.synchronize()
+            assert torch.equal(pm_b[i * parts:(i + 1) * parts, :n_img], pm[:, :n_img]), (nb, i)
+            assert torch.equal(pz_b[i * parts:(i + 1) * parts, :n_img], pz[:, :n_img]), (nb, i)
+            m, z = sx.ops.score_merge(pm, pz, n_img)
+            ms.append(m)
+            zs.append(z)
+        scores_b = sx.ops.score_pass2_batch(keys, q, torch.stack(ms), torch.stack(zs), n_img)
+        for i in range(nb):
+            s, _ = sx.ops.score_pass2(keys, q[i, :n_img].contiguous(), ms[i], zs[i], sx.ops.SCORE_TC)
+            torch.cuda.synchronize()
+            assert torch.equal(scores_b[i], s), (nb, i)
+        assert abs(scores_b.double().sum(1) - n_img).max().item() < 1e-2 * n_img
+
+
+def test_multi_query_pipeline_equals_per_query_pipeline(sx, synthetic):
+    """ShardedPoseEstimator(multi_query=True) end to end on one GPU: same poses as the per-query pipeline"""
+    from conftest import load_golden
+    dev = "cuda"
+    g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
+    ori, dirs, rgb = r["ori"].to(dev), r["dirs"].to(dev), r["rgb"].to(dev)
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone(), score_impl="tc_bf16")
+    idm.load_state_dict(synthetic.synth_id_weights(seed=g["weight_seed"]), strict=False)
+    idm = idm.to(dev).eval().requires_grad_(False)
+    img = g["img"].to(dev)
+    imgs = torch.stack((img, img.flip(1), img * 0.7))
+    masks = torch.stack((torch.ones(64, 64, dtype=torch.bool, device=dev), g["mask2"].to(dev),
+                         torch.ones(64, 64, dtype=torch.bool, device=dev)))
+    cache = idm.build_key_cache(ori, dirs, rgb)
+    ref, _ = sx.ShardedPoseEstimator(idm, ori, dirs, cache).query_batch(imgs, masks)
+    est = sx.ShardedPoseEstimator(idm, ori, dirs, cache, multi_query=True)
+    out, _ = est.query_batch(imgs, masks)
+    torch.testing.assert_close(out, ref, rtol=0, atol=0)
+    assert est.enable_cuda_graphs(imgs, masks)
+    out_g, _ = est.query_batch(imgs, masks)
+    torch.testing.assert_close(out_g, ref, rtol=0, atol=0)

@@ -80,7 +80,28 @@ class OracleBackend:
         return c2w, torch.zeros(8)
 
 
-def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=False):
+class OracleBatchBackend(OracleBackend):
+    """adds the several-queries-per-sweep entry points (same results as the per-query calls, one call per batch)"""
+    impl = 1  # what ShardedPoseEstimator(multi_query=True) requires of its backend
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self.batch_calls = 0
+
+    def pass1_batch(self, keys, q):
+        assert q.is_contiguous()
+        self.batch_calls += 1
+        parts = [self.pass1(keys, q[i]) for i in range(q.shape[0])]
+        return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+
+    def pass2_batch(self, keys, q, m, z, out):
+        self.batch_calls += 1
+        for i in range(q.shape[0]):
+            self.pass2(keys, q[i], m[i], z[i], out[i])
+        return out
+
+
+def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=False, multi_query=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -99,9 +120,9 @@ def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=Fal
     keys = torch.nn.functional.linear(oracle.ray_features(ori[lo:hi], dirs[lo:hi], rgb[lo:hi], w),
                                       w["attention.k_proj.weight"], w["attention.k_proj.bias"])
     cache = sx.RayKeyCache(keys, hi - lo, ())
-    be = OracleBackend(oracle, w, g["tok_pe"], g["up"])
+    be = (OracleBatchBackend if multi_query else OracleBackend)(oracle, w, g["tok_pe"], g["up"])
     est = sx.ShardedPoseEstimator(None, ori[lo:hi].contiguous(), dirs[lo:hi].contiguous(), cache, rank, world, backend=be,
-                                  front_end=front_end)
+                                  front_end=front_end, multi_query=multi_query)
     imgs = torch.arange(nb, dtype=torch.float32)[:, None, None, None].expand(nb, 2, 2, 3).contiguous()
     masks = torch.ones(nb, 2, 2, dtype=torch.bool)
     if local:  # hand over this rank's images only
@@ -110,6 +131,7 @@ def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=Fal
     c2w, _ = est.query_batch(imgs, masks, k=100, local=local)
     shards = front_end == "sharded" and nb % world == 0
     assert be.front_batches == [nb // world if shards else nb]  # the front end ran once, on this rank's share
+    assert getattr(be, "batch_calls", 0) == (2 if multi_query else 0)  # one call per pass for the whole batch
     # every rank must hold the same poses
     gathered = [torch.empty_like(c2w) for _ in range(world)]
     dist.all_gather(gathered, c2w)
@@ -122,12 +144,13 @@ def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=Fal
 # replicated front end, batch 3; sharded front end with an odd batch (falls back to replicated), with an even batch
 # given whole, and with each rank given only its own images
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("nb,front_end,local", [(3, "replicated", False), (3, "sharded", False),
-                                                (4, "sharded", False), (4, "sharded", True)])
-def test_two_rank_sharded_query_matches_single_process(oracle, synthetic, tmp_path, nb, front_end, local):
+@pytest.mark.parametrize("nb,front_end,local,multi_query", [(3, "replicated", False, False), (3, "sharded", False, False),
+                                                            (4, "sharded", False, False), (4, "sharded", True, False),
+                                                            (3, "replicated", False, True), (4, "sharded", True, True)])
+def test_two_rank_sharded_query_matches_single_process(oracle, synthetic, tmp_path, nb, front_end, local, multi_query):
     from conftest import load_golden
     out = str(tmp_path / "c2w.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out, nb, front_end, local), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, nb, front_end, local, multi_query), nprocs=2, join=True)
     c2w = torch.load(out)
     assert c2w.shape == (nb, 4, 4)
     g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
@@ -157,5 +180,7 @@ def test_single_rank_path_uses_no_collective(sx, oracle, synthetic):
         est.query_batch(torch.zeros(1, 2, 2, 3), torch.ones(1, 2, 2, dtype=torch.bool), local=True)
     with pytest.raises(ValueError):
         sx.ShardedPoseEstimator(None, r["ori"], r["dirs"], est.cache, 0, 1, backend=est.backend, front_end="rank0")
+    with pytest.raises(ValueError):  # the batched sweep exists on the tensor-core path only
+        sx.ShardedPoseEstimator(None, r["ori"], r["dirs"], est.cache, 0, 1, backend=est.backend, multi_query=True)
     ref, _ = oracle.pose_tail(g["topk_idx"], g["topk_vals"], r["ori"], r["dirs"], g["up"])
     torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
