@@ -306,12 +306,12 @@ def main():
     mask_dev = torch.ones(B, args.height, args.width, dtype=torch.bool, device=dev)
 
     # front_end="sharded": every rank holds (and, in the e2e leg, uploads) only its own B/world images
-    local = args.front_end == "sharded" and world > 1 and B % world == 0
-    lo, hi = (rank * (B // world), (rank + 1) * (B // world)) if local else (0, B)
+    own_only = args.front_end == "sharded" and world > 1 and B % world == 0
+    lo, hi = (rank * (B // world), (rank + 1) * (B // world)) if own_only else (0, B)
     img_q, mask_q = img_dev[lo:hi], mask_dev[lo:hi]
 
     def query():
-        return est.query_batch(img_q, mask_q, local=local)
+        return est.query_batch(img_q, mask_q, local=own_only)
 
     # one-query-per-step latency figure (eager + its own graphs), measured before the batched graphs are captured
     lat_b1 = None
@@ -339,7 +339,7 @@ def main():
     burst1, burst2 = time_score_kernels(sx, idm, cache, dev, 2, 4)
     graph = False
     if not args.no_graph:
-        graph = est.enable_cuda_graphs(img_q, mask_q, local=local)
+        graph = est.enable_cuda_graphs(img_q, mask_q, local=own_only)
         if graph:
             g_out = query()
             torch.cuda.synchronize()
@@ -388,7 +388,7 @@ def main():
         d = img_host_q.to(dev, non_blocking=True)
         torch.div(d, 255.0, out=img_e2e)  # uint8 -> [0,1] float (test.py:69-73)
         m = torch.ones_like(img_e2e[..., 0], dtype=torch.bool)
-        c, _ = est.query_batch(img_e2e, m, local=local)
+        c, _ = est.query_batch(img_e2e, m, local=own_only)
         pose_host.copy_(c, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
