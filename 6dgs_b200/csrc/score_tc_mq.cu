@@ -378,7 +378,7 @@ extern "C" int sixdgs_score_pass1_batch(const void* k_cache, int k_dtype, int64_
                                         void* stream) {
   SIXDGS_REQUIRE(k_cache && q && part_m && part_z, "null pointer");
   SIXDGS_REQUIRE(k_dtype == SIXDGS_BF16, "the batched path needs a bf16 key cache");
-  SIXDGS_REQUIRE(n_rays >= 0 && n_img >= 1 && n_img <= kMaxTokens, "bad sizes");
+  SIXDGS_REQUIRE(n_rays >= 1 && n_img >= 1 && n_img <= kMaxTokens, "bad sizes");
   return mq_launch<1>(k_cache, n_rays, q, n_queries, n_img, part_m, part_z, nullptr, nullptr, nullptr, 0, workspace,
                       workspace_bytes, (cudaStream_t)stream);
 }
@@ -388,7 +388,7 @@ extern "C" int sixdgs_score_pass2_batch(const void* k_cache, int k_dtype, int64_
                                         void* workspace, size_t workspace_bytes, void* stream) {
   SIXDGS_REQUIRE(k_cache && q && m && z && scores, "null pointer");
   SIXDGS_REQUIRE(k_dtype == SIXDGS_BF16, "the batched path needs a bf16 key cache");
-  SIXDGS_REQUIRE(n_rays >= 0 && n_img >= 1 && n_img <= kMaxTokens && score_stride >= n_rays, "bad sizes");
+  SIXDGS_REQUIRE(n_rays >= 1 && n_img >= 1 && n_img <= kMaxTokens && score_stride >= n_rays, "bad sizes");
   return mq_launch<2>(k_cache, n_rays, q, n_queries, n_img, nullptr, nullptr, m, z, scores, score_stride, workspace,
                       workspace_bytes, (cudaStream_t)stream);
 }
