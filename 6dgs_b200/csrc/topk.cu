@@ -124,6 +124,69 @@ topk_final_kernel(TopkState* st, const uint32_t* __restrict__ ckey, const int64_
   if (t < k) { vals[t] = key2f(skey[t]); idx[t] = sidx[t]; }
 }
 
+// EXPERIMENTAL variant (sixdgs_topk_fused): the digit selection runs in the LAST histogram CTA to finish (atomic
+// ticket) with a 256-thread suffix scan, instead of a single-thread kernel per pass: 7 launches instead of 11 and no
+// 10 us serial bin walks -- matters when the shard is small (8 GPUs: 3.6 M scores, the four sweeps take ~4 us each).
+struct TopkStateFused {
+  TopkState st;
+  uint32_t ticket[4];
+};
+
+__global__ void topk_init_fused_kernel(TopkStateFused* sf, int k) {
+  const int t = threadIdx.x;
+  for (int i = t; i < 4 * 256; i += blockDim.x) (&sf->st.hist[0][0])[i] = 0;
+  if (t < 4) sf->ticket[t] = 0;
+  if (t == 0) { sf->st.prefix = 0; sf->st.mask = 0; sf->st.k_rem = (uint32_t)k; sf->st.n_gt = 0; sf->st.n_eq = 0; }
+}
+
+__global__ void __launch_bounds__(256)
+topk_hist_select_kernel(const float* __restrict__ x, int64_t n, TopkStateFused* sf, int pass) {
+  __shared__ uint32_t h[256];
+  __shared__ uint32_t wsum[8];
+  __shared__ bool last;
+  TopkState* st = &sf->st;
+  const int t = threadIdx.x;
+  h[t] = 0;
+  __syncthreads();
+  const uint32_t prefix = st->prefix, mask = st->mask;
+  const int shift = 24 - 8 * pass;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + t; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t u = f2key(x[i]);
+    if ((u & mask) == prefix) atomicAdd(&h[(u >> shift) & 0xffu], 1u);
+  }
+  __syncthreads();
+  if (h[t]) atomicAdd(&st->hist[pass][t], h[t]);
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last = atomicAdd(&sf->ticket[pass], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // inclusive suffix sums S[d] = sum_{j >= d} hist[j]; the digit is the largest d with S[d] >= k_rem
+  const uint32_t c = atomicAdd(&st->hist[pass][t], 0u);  // L2 read of the completed histogram
+  const int lane = t & 31, w = t >> 5;
+  uint32_t v = c;  // suffix scan inside the warp (towards higher lanes)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_down_sync(0xffffffffu, v, o);
+    if (lane + o < 32) v += up;
+  }
+  if (lane == 0) wsum[w] = v;
+  __syncthreads();
+  uint32_t higher = 0;  // counts in the warps above this one
+  for (int j = w + 1; j < 8; ++j) higher += wsum[j];
+  const uint32_t S = v + higher;      // elements with digit >= t
+  const uint32_t above = S - c;       // elements with digit >  t
+  const uint32_t k_rem = st->k_rem;
+  __syncthreads();                    // everyone has read k_rem before it is rewritten
+  const bool hit = (S >= k_rem && above < k_rem) || (t == 0 && S < k_rem);  // digit 0 also catches "fewer than k left"
+  if (hit) {
+    st->prefix = prefix | ((uint32_t)t << shift);
+    st->mask = mask | (0xffu << shift);
+    st->k_rem = k_rem - above;
+  }
+}
+
 // n <= 4096 (e.g. the cross-rank candidate table, world * k rows): one CTA, one launch -- load everything,
 // bitonic sort by (key desc, index asc), emit the first k.  Same ordering as the radix path.
 constexpr int kSmallN = 4096;
@@ -164,6 +227,38 @@ using namespace sixdgs;
 extern "C" size_t sixdgs_topk_workspace(int64_t n, int k) {
   (void)n;
   return sizeof(TopkState) + (size_t)k * (sizeof(uint32_t) + sizeof(int64_t)) + kTieCap * sizeof(int64_t) + 64;
+}
+
+extern "C" size_t sixdgs_topk_fused_workspace(int64_t n, int k) { return sixdgs_topk_workspace(n, k) + 64; }
+
+// EXPERIMENTAL: same contract and results as sixdgs_topk, 7 launches instead of 11 (selection fused into the sweeps)
+extern "C" int sixdgs_topk_fused(const float* scores, int64_t n, int k, float* vals, int64_t* idx, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  SIXDGS_REQUIRE(scores && vals && idx && workspace, "null pointer");
+  SIXDGS_REQUIRE(k >= 1 && k <= kTopkMaxK, "k must be in [1, 1024]");
+  SIXDGS_REQUIRE(n >= k, "selected index k out of range");
+  if (workspace_bytes < sixdgs_topk_fused_workspace(n, k)) {
+    set_error("topk_fused: workspace too small");
+    return SIXDGS_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n <= kSmallN) {
+    topk_small_kernel<<<1, 1024, 0, s>>>(scores, (int)n, k, vals, idx);
+    return check_launch("topk_small");
+  }
+  unsigned char* w = (unsigned char*)workspace;
+  TopkStateFused* sf = (TopkStateFused*)w;
+  w += sizeof(TopkStateFused) + (64 - sizeof(TopkStateFused) % 64) % 64;
+  int64_t* cidx = (int64_t*)w; w += (size_t)k * sizeof(int64_t);
+  int64_t* tie = (int64_t*)w; w += kTieCap * sizeof(int64_t);
+  uint32_t* ckey = (uint32_t*)w;
+  const int64_t want = (n + 256 * 8 - 1) / (256 * 8);
+  const unsigned grid = (unsigned)(want < kNumSMs * 8 ? (want > 0 ? want : 1) : kNumSMs * 8);
+  topk_init_fused_kernel<<<1, 256, 0, s>>>(sf, k);
+  for (int p = 0; p < 4; ++p) topk_hist_select_kernel<<<grid, 256, 0, s>>>(scores, n, sf, p);
+  topk_gather_kernel<<<grid, 256, 0, s>>>(scores, n, &sf->st, ckey, cidx, tie, k);
+  topk_final_kernel<<<1, 1024, 0, s>>>(&sf->st, ckey, cidx, tie, k, vals, idx);
+  return check_launch("topk_fused");
 }
 
 extern "C" int sixdgs_topk(const float* scores, int64_t n, int k, float* vals, int64_t* idx, void* workspace,

@@ -301,13 +301,15 @@ def score_pass2_batch(k_cache: torch.Tensor, q: torch.Tensor, m: torch.Tensor, z
     return scores
 
 
-def topk(scores: torch.Tensor, k: int):
+def topk(scores: torch.Tensor, k: int, fused: bool = False):
+    """fused=True: EXPERIMENTAL variant with the digit selection inside the histogram sweeps (same results)"""
     n = scores.shape[0]
     vals = torch.empty(k, dtype=torch.float32, device=scores.device)
     idx = torch.empty(k, dtype=torch.int64, device=scores.device)
-    wsz = int(_lib.load().sixdgs_topk_workspace(n, k))
+    fn = "sixdgs_topk_fused" if fused else "sixdgs_topk"
+    wsz = int(getattr(_lib.load(), fn + "_workspace")(n, k))
     ws = torch.empty(wsz, dtype=torch.uint8, device=scores.device)
-    call("sixdgs_topk", dptr(scores), n, k, dptr(vals), dptr(idx, torch.int64), dptr(ws, torch.uint8), wsz, stream_ptr())
+    call(fn, dptr(scores), n, k, dptr(vals), dptr(idx, torch.int64), dptr(ws, torch.uint8), wsz, stream_ptr())
     return vals, idx
 
 

@@ -23,8 +23,9 @@ from . import _lib, ops
 class CudaBackend:
     """The product backend: every call lands in libsixdgs.so."""
 
-    def __init__(self, idm):
+    def __init__(self, idm, fused_topk: bool = False):
         self.idm = idm
+        self.fused_topk = bool(fused_topk)  # EXPERIMENTAL: sixdgs_topk_fused (7 launches instead of 11)
         self.impl = idm._impl
         self.parts = int(_lib.load().sixdgs_score_parts(self.impl))
 
@@ -62,7 +63,7 @@ class CudaBackend:
         return ops.score_pass2_batch(keys, q, m, z, out=out)
 
     def topk(self, scores, k):
-        return ops.topk(scores, k)
+        return ops.topk(scores, k, fused=self.fused_topk)
 
     def camera_up(self, grid):
         """[B,384,16,16] -> unit up vectors [B,3]"""
@@ -110,7 +111,8 @@ class ShardedPoseEstimator:
         # (11; 1 when the shard has <= 4096 rays), pose tail 1, and when sharded candidate pack 1 + global top-k 1.
         # The q projection is one launch per batch (launches_per_batch).
         tc = 2 if getattr(self.backend, "impl", 0) == ops.SCORE_TC else 0
-        self.launches_per_query = 3 + tc + (11 if cache.n_rays > 4096 else 1) + 1 + (2 if world > 1 else 0)
+        radix = 7 if getattr(self.backend, "fused_topk", False) else 11
+        self.launches_per_query = 3 + tc + (radix if cache.n_rays > 4096 else 1) + 1 + (2 if world > 1 else 0)
         self.launches_per_batch = 1
         if self.multi_query:  # per query only the merge remains; per batch (of <= 8) q-prep + kernel for each pass
             self.launches_per_query -= 2 + tc

@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--front-end", choices=("replicated", "sharded"), default="replicated",
                     help="N>1: every rank runs the image front end for the whole batch, or only for its B/N images "
                          "(one more all-gather per batch; the e2e leg then uploads each image once)")
+    ap.add_argument("--fused-topk", action="store_true", help="EXPERIMENTAL: sixdgs_topk_fused (7 launches instead of 11)")
     ap.add_argument("--multi-query", action="store_true",
                     help="EXPERIMENTAL: score the whole batch in one sweep over the key cache per pass (score_tc_mq.cu)")
     ap.add_argument("--batch", type=int, default=8,
@@ -297,7 +298,8 @@ def main():
         dist.all_reduce(t)
         n_total = int(t.item())
     est = sharding.ShardedPoseEstimator(idm, ori, dirs, cache, rank, world, front_end=args.front_end,
-                                        multi_query=args.multi_query)
+                                        multi_query=args.multi_query,
+                                        backend=sharding.CudaBackend(idm, fused_topk=args.fused_topk))
 
     B = args.batch
     img_u8 = torch.stack([(sx.synthetic.synth_image(args.height, args.width, seed=7 + i) * 255).to(torch.uint8) for i in range(B)])

@@ -162,6 +162,10 @@ int sixdgs_score_pass2_batch(const void* k_cache, int k_dtype, int64_t n_rays, c
 size_t sixdgs_topk_workspace(int64_t n, int k);
 int sixdgs_topk(const float* scores, int64_t n, int k, float* vals, int64_t* idx, void* workspace,
                 size_t workspace_bytes, void* stream);
+/* EXPERIMENTAL: same contract and results, digit selection fused into the histogram sweeps (7 launches, not 11) */
+size_t sixdgs_topk_fused_workspace(int64_t n, int k);
+int sixdgs_topk_fused(const float* scores, int64_t n, int k, float* vals, int64_t* idx, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ---- a13: least-squares line intersection -------- line_intersection.py:75-154 ------------------
  * R = sum w (I - d d^T), q = sum w (I - d d^T) o, centre = solve(R, q); NaN x3 and *status |= 1 when

@@ -144,3 +144,28 @@ def test_multi_query_pipeline_equals_per_query_pipeline(sx, synthetic):
     assert est.enable_cuda_graphs(imgs, masks)
     out_g, _ = est.query_batch(imgs, masks)
     torch.testing.assert_close(out_g, ref, rtol=0, atol=0)
+
+
+def test_fused_select_topk_equals_validated_topk(sx):
+    """sixdgs_topk_fused (selection in the last histogram CTA) against sixdgs_topk and torch.topk: values, indices and
+    tie order, incl. heavy ties, negative / denormal / inf values and sizes around the single-CTA threshold"""
+    dev = "cuda"
+    gen = torch.Generator().manual_seed(5)
+    cases = []
+    for n in (4097, 5000, 100_000, 3_600_000):
+        cases.append(torch.rand(n, generator=gen))
+        cases.append(torch.randn(n, generator=gen) * 1e-3)
+        cases.append(torch.randint(0, 7, (n,), generator=gen).float())          # heavy ties
+        x = torch.randn(n, generator=gen)
+        x[::1001] = float("inf")
+        x[5::1003] = -float("inf")
+        x[7::1009] = 1e-42                                                        # denormals
+        cases.append(x)
+    for x in cases:
+        x = x.to(dev)
+        for k in (1, 100, 1024):
+            v0, i0 = sx.ops.topk(x, k)
+            v1, i1 = sx.ops.topk(x, k, fused=True)
+            torch.cuda.synchronize()
+            assert torch.equal(v0, v1) and torch.equal(i0, i1), (x.shape[0], k)
+            assert torch.equal(v1, torch.topk(x, k).values)

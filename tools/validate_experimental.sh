@@ -13,3 +13,4 @@ step 120 python -m pytest tests/test_experimental.py -q -x --timeout 100 -k "mul
 step 240 python -m pytest tests/test_experimental.py -q --timeout 200
 step 120 python tools/mq_probe.py --rays 12000000 --batch 8 --seconds 4
 step 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --multi-query
+step 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --fused-topk
