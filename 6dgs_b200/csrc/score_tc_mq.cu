@@ -1,6 +1,12 @@
-// a11, several queries per key sweep (SURVEY §8d "ray-score, batch" row).  EXPERIMENTAL: built and exported, not on
-// any default path until it has been validated and timed on a B200 (tests/test_experimental.py).
-// Reference: pose_estimation/our_multihead_attention.py:4-12,70-79; identification_module.py:80-82.
+// a11, several queries per key sweep (SURVEY §8d "ray-score, batch" row), in two key formats:
+//   bf16   (SPLIT = false): one MMA term, 768 B/ray -- the throughput mode (3e-2 score tolerance);
+//   f16x2  (SPLIT = true):  every key and every query element is carried as an fp16 pair hi + lo (22 significant
+//          bits) and the logit is the three-term product  Qh.Kh + Qh.Kl + Ql.Kh  accumulated in one fp32 TMEM
+//          accumulator (the dropped Ql.Kl term is 2^-22 relative) -- the EXACT tensor-core mode: scores agree with the
+//          fp32 reference to ~1e-5 even for a peaked (trained) softmax where bf16 logits are off by 1e-1.
+// Validated on B200 in round 2 (bit-identical to score_tc.cu in bf16 mode; profiles/validate_experimental_r2.log).
+// Reference: pose_estimation/our_multihead_attention.py:4-12,70-79; identification_module.py:80-82;
+// fused all-ray weighted least squares: least_squared_loss.py:47-64, line_intersection.py:75-154.
 //
 // Why.  score_tc.cu streams the whole bf16 key cache from HBM twice per query.  At 256 FLOP/B that kernel sits on
 // the B200 ridge and, run back to back, is limited by board power -- and roughly a quarter of that
@@ -19,6 +25,17 @@
 //     private to each epilogue thread; pass 2: D = K Q^T (lanes = rays), c_token per query in shared memory.
 //   * warp roles: 0 = key producer, 3 = token producer, 1 = MMA issuer (leader CTA), 2 = TMEM allocator,
 //     4..11 = epilogue.
+// f16x2 layout: a cache row is [hi(384) | lo(384)] fp16 (1536 B) holding 16*k; the query workspace rows are laid out
+// the same way and hold 64*log2(e)/sqrt(384)*q, so the accumulator is 2^10 * logit*log2(e) and the epilogue multiplies
+// by 2^-10 inside the FMA that subtracts the softmax offset (power-of-two scales: exact; they keep the lo halves out
+// of the fp16 subnormal range).  The resident slices are the hi halves (96 KB); the ring (7 stages) carries, per
+// k-block of a query, the query's hi block, the tile's lo key block (HBM once, then L2 for the other queries of the
+// batch) and the query's lo block -- 288 KB per (tile, query) against three times the MMA work of the bf16 mode, i.e.
+// the same L2 -> SM rate.
+// Optional pass-2 epilogue: the all-ray weighted least-squares system of least_squared_loss.py:62-64
+// (weights = score / n_img) -- per-CTA fp64 partial sums of R (6), q (3), sum w d (3), sum w (1) from the scores the
+// epilogue already holds (+24 B/ray for origin and direction), reduced by sixdgs_ls_reduce / one 13-double allreduce.
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace sixdgs {
@@ -26,7 +43,7 @@ namespace sixdgs {
 namespace {
 
 constexpr int kMqMaxQ = 8;
-constexpr int kMqStages = 6;
+constexpr int kMqLs = 13;  // R (xx,xy,xz,yy,yz,zz), q (3), sum w d (3), sum w
 constexpr int kMqTileRays = 256;
 constexpr int kMqKBlocks = kFeat / 64;  // 6
 constexpr int kMqKBBytes = 128 * 128;   // 128 rows x 128 B
@@ -36,33 +53,47 @@ constexpr float kMqLog2e = 1.4426950408889634f;
 constexpr float kMqLn2 = 0.6931471805599453f;
 constexpr float kMqQScale = 1.4426950408889634f / 19.595917942265423f;  // log2(e) / sqrt(384)
 
-struct __align__(1024) MqSmem {
-  uint8_t kt[kMqKBlocks][kMqKBBytes];  //  96 KB: this CTA's 128 rays of the current tile
-  uint8_t qs[kMqStages][kMqKBBytes];   //  96 KB: token ring
+template <bool SPLIT>
+struct MqCfg {
+  static constexpr int kStages = SPLIT ? 7 : 6;
+  static constexpr int kRow = SPLIT ? 2 * kFeat : kFeat;          // elements per cache / query row
+  static constexpr uint32_t kIdesc = umma_idesc(SPLIT ? 0u : 1u, 256, 256);  // fp16 or bf16 -> fp32, M = N = 256
+};
+constexpr float kMqKeyScale = 16.0f;                 // f16x2: stored key = 16 k
+constexpr float kMqQryScale = 64.0f;                 // f16x2: stored query = 64 log2(e)/sqrt(384) q
+constexpr float kMqSplitOut = 1.0f / 1024.0f;        // accumulator -> log2-domain logit
+
+// (no struct-level alignment attribute: the kernel aligns the base to 1024 B by hand and sizeof must not be padded --
+// the f16x2 variant uses all but 768 B of the 227 KB a CTA can have)
+template <int STAGES>
+struct MqSmem {
+  uint8_t kt[kMqKBlocks][kMqKBBytes];  //  96 KB: this CTA's 128 rays of the current tile (f16x2: the hi halves)
+  uint8_t qs[STAGES][kMqKBBytes];      //  96 / 112 KB: token ring (f16x2: query hi, key lo, query lo blocks)
   uint64_t k_full[kMqKBlocks];
   uint64_t k_empty[kMqKBlocks];
-  uint64_t q_full[kMqStages];
-  uint64_t q_empty[kMqStages];
+  uint64_t q_full[STAGES];
+  uint64_t q_empty[STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  union __align__(16) {
-    float cst[kMqMaxQ][kMaxTokens];   // pass 2: c_token = m*log2e + log2 z per query (+inf: token unused)
-    float2 stat[kMqMaxQ][2][128];     // pass 1: (running max, running sum) per query / column half / token row
+  union alignas(16) {
+    struct {
+      float cst[kMqMaxQ][kMaxTokens];  // pass 2: c_token = m*log2e + log2 z per query (+inf: token unused)
+      double ls[kMqMaxQ][4][kMqLs];    // pass 2, fused LS: per (query, half-0 epilogue warp) partial sums
+    };
+    float2 stat[kMqMaxQ][2][128];      // pass 1: (running max, running sum) per query / column half / token row
   };
-  float xch[2][128];
-  float xch2[2][128];
+  float xch[2][128];                   // column-half exchange (pass 1's final merge borrows ring stage 0 for a second one)
 };
+static_assert(sizeof(MqSmem<7>) + 1024 <= 232448, "f16x2 variant exceeds the 227 KB shared-memory limit");
 
-constexpr uint32_t kMqIdesc = umma_idesc(1, 256, 256);  // bf16 x bf16 -> fp32, M = 256 over the pair, N = 256
-
-__device__ __forceinline__ void mq_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void mq_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(kMqIdesc), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ float mq_ex2(float x) {
@@ -73,7 +104,8 @@ __device__ __forceinline__ float mq_ex2(float x) {
 __device__ __forceinline__ void mq_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // fold 32 logits (one TMEM chunk) of one token into its running (max, sum-exp2); nv = real rays in the chunk
-__device__ __forceinline__ void mq_fold(const float (&cur)[32], int nv, float& run_m, float& run_z) {
+// (sc = accumulator -> log2-logit scale; 1 in bf16 mode, where fmaf(x, 1, -m) == x - m bit for bit)
+__device__ __forceinline__ void mq_fold(const float (&cur)[32], int nv, float& run_m, float& run_z, const float sc) {
   if (nv >= 32) {
     float m0 = fmaxf(cur[0], cur[1]), m1 = fmaxf(cur[2], cur[3]), m2 = fmaxf(cur[4], cur[5]), m3 = fmaxf(cur[6], cur[7]);
 #pragma unroll
@@ -83,14 +115,14 @@ __device__ __forceinline__ void mq_fold(const float (&cur)[32], int nv, float& r
       m2 = fmaxf(m2, fmaxf(cur[j + 4], cur[j + 5]));
       m3 = fmaxf(m3, fmaxf(cur[j + 6], cur[j + 7]));
     }
-    const float mn = fmaxf(fmaxf(run_m, fmaxf(m0, m1)), fmaxf(m2, m3));
+    const float mn = fmaxf(run_m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sc);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      s0 += mq_ex2(cur[j + 0] - mn);
-      s1 += mq_ex2(cur[j + 1] - mn);
-      s2 += mq_ex2(cur[j + 2] - mn);
-      s3 += mq_ex2(cur[j + 3] - mn);
+      s0 += mq_ex2(fmaf(cur[j + 0], sc, -mn));
+      s1 += mq_ex2(fmaf(cur[j + 1], sc, -mn));
+      s2 += mq_ex2(fmaf(cur[j + 2], sc, -mn));
+      s3 += mq_ex2(fmaf(cur[j + 3], sc, -mn));
     }
     run_z = run_z * mq_ex2(run_m - mn) + ((s0 + s1) + (s2 + s3));
     run_m = mn;
@@ -98,10 +130,10 @@ __device__ __forceinline__ void mq_fold(const float (&cur)[32], int nv, float& r
     float cm = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (j < nv) ? cur[j] : -INFINITY);
-    const float mn = fmaxf(run_m, cm);
+    const float mn = fmaxf(run_m, cm * sc);
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s += (j < nv) ? mq_ex2(cur[j] - mn) : 0.f;
+    for (int j = 0; j < 32; ++j) s += (j < nv) ? mq_ex2(fmaf(cur[j], sc, -mn)) : 0.f;
     run_z = run_z * mq_ex2(run_m - mn) + s;
     run_m = mn;
   }
@@ -114,22 +146,60 @@ __global__ void mq_qprep_kernel(const float* __restrict__ q, int n_img, int nq, 
   const int t = (int)((i / kFeat) % kMaxTokens);
   qb[i] = __float2bfloat16_rn(t < n_img ? q[i] * kMqQScale : 0.0f);
 }
+// f16x2: row [hi(384) | lo(384)] of 64 * log2(e)/sqrt(384) * q   (hi = fp16(x), lo = fp16(x - hi))
+__global__ void mq_qprep_split_kernel(const float* __restrict__ q, int n_img, int nq, __half* __restrict__ qb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)nq * kMaxTokens * kFeat) return;
+  const int64_t row = i / kFeat;
+  const int col = (int)(i % kFeat);
+  const int t = (int)(row % kMaxTokens);
+  const float x = t < n_img ? q[i] * (kMqQScale * kMqQryScale) : 0.0f;
+  const __half hi = __float2half_rn(x);
+  qb[row * (2 * kFeat) + col] = hi;
+  qb[row * (2 * kFeat) + kFeat + col] = __float2half_rn(x - __half2float(hi));
+}
+// fp32 keys [n,384] -> f16x2 rows [n, 768] = [hi | lo] of 16 k; absmax (nullable) receives max |16 k| (as float bits)
+__global__ void mq_split_keys_kernel(const float* __restrict__ k, int64_t n, __half* __restrict__ out,
+                                     unsigned int* __restrict__ absmax) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float a = 0.f;
+  if (i < n * kFeat) {
+    const int64_t row = i / kFeat;
+    const int col = (int)(i % kFeat);
+    const float x = k[i] * kMqKeyScale;
+    const __half hi = __float2half_rn(x);
+    out[row * (2 * kFeat) + col] = hi;
+    out[row * (2 * kFeat) + kFeat + col] = __float2half_rn(x - __half2float(hi));
+    a = fabsf(x);
+    if (!(a == a)) a = INFINITY;  // NaN keys must trip the range check too
+  }
+  if (absmax) {
+    a = warp_max(a);
+    if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(absmax, __float_as_uint(a));  // non-negative floats order as uints
+  }
+}
 
-template <int PASS>
+template <int PASS, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMqThreads, 1)
 score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_q,
                    int64_t n_rays, int n_img, int nq,
                    float* __restrict__ part_m, float* __restrict__ part_z,      // pass 1 out [nq, pairs, 256]
                    const float* __restrict__ gm, const float* __restrict__ gz,  // pass 2 in  [nq, 256]
-                   float* __restrict__ scores, int64_t score_stride) {          // pass 2 out [nq, score_stride]
+                   float* __restrict__ scores, int64_t score_stride,            // pass 2 out [nq, score_stride]
+                   const float* __restrict__ rays_ori, const float* __restrict__ rays_dir,  // pass 2, fused LS (nullable)
+                   double* __restrict__ ls_part) {                              // pass 2 out [nq, 2*pairs, 13]
+  using Cfg = MqCfg<SPLIT>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr float kSc = SPLIT ? kMqSplitOut : 1.0f;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  MqSmem& sm = *reinterpret_cast<MqSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  MqSmem<kStages>& sm = *reinterpret_cast<MqSmem<kStages>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
   const int n_pairs = gridDim.x >> 1;
   const int64_t n_tiles = (n_rays + kMqTileRays - 1) / kMqTileRays;
+  const bool fuse_ls = PASS == 2 && ls_part != nullptr;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_k)) : "memory");
@@ -140,7 +210,7 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
       mbar_init(&sm.k_full[s], 2);   // leader's expect_tx arrive + peer's remote arrive
       mbar_init(&sm.k_empty[s], 1);  // one multicast tcgen05.commit (after the tile's last query)
     }
-    for (int s = 0; s < kMqStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm.q_full[s], 2);
       mbar_init(&sm.q_empty[s], 1);
     }
@@ -161,6 +231,7 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
       const int t = i % kMaxTokens;
       (&sm.cst[0][0])[i] = (t < n_img) ? (gm[i] * kMqLog2e + log2f(gz[i])) : INFINITY;
     }
+    for (int i = tid; i < kMqMaxQ * 4 * kMqLs; i += kMqThreads) (&sm.ls[0][0][0])[i] = 0.0;
   } else {
     for (int i = tid; i < nq * 2 * 128; i += kMqThreads) (&sm.stat[0][0][0])[i] = make_float2(-INFINITY, 0.f);
   }
@@ -171,7 +242,7 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
   const uint32_t tmem_base = sm.tmem_base;
 
   if (warp == 0) {
-    // ================================ key producer (both CTAs) ================================
+    // ================================ key producer (both CTAs): the resident (hi) slices ================================
     if (lane == 0) {
       uint32_t phase = 0;
       for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
@@ -187,19 +258,28 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     }
     __syncwarp();
   } else if (warp == 3) {
-    // ================================ token producer (both CTAs) ================================
+    // ================================ ring producer (both CTAs) ================================
+    // bf16: the query's k-block.  f16x2: query hi block, key lo block of the tile, query lo block.
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      auto push = [&](const CUtensorMap* map, int c0, int c1) {
+        mbar_wait(&sm.q_empty[stage], phase ^ 1);
+        if (leader) mbar_arrive_expect_tx(&sm.q_full[stage], 2 * kMqKBBytes);
+        else mbar_arrive_cluster(&sm.q_full[stage], 0);
+        tma_load_2sm(sm.qs[stage], map, &sm.q_full[stage], c0, c1);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      };
       for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
+        const int krow0 = (int)(tile * kMqTileRays + rank * 128);
         for (int b = 0; b < nq; ++b) {
           const int row0 = b * kMaxTokens + (int)rank * 128;
           for (int kb = 0; kb < kMqKBlocks; ++kb) {
-            mbar_wait(&sm.q_empty[stage], phase ^ 1);
-            if (leader) mbar_arrive_expect_tx(&sm.q_full[stage], 2 * kMqKBBytes);
-            else mbar_arrive_cluster(&sm.q_full[stage], 0);
-            tma_load_2sm(sm.qs[stage], &tmap_q, &sm.q_full[stage], kb * 64, row0);
-            if (++stage == kMqStages) { stage = 0; phase ^= 1; }
+            push(&tmap_q, kb * 64, row0);
+            if (SPLIT) {
+              push(&tmap_k, kFeat + kb * 64, krow0);
+              push(&tmap_q, kFeat + kb * 64, row0);
+            }
           }
         }
       }
@@ -211,6 +291,18 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
       int stage = 0;
       uint32_t qphase = 0, kphase = 0;
       int64_t it = 0;  // (tile, query) counter
+      auto next = [&]() { if (++stage == kStages) { stage = 0; qphase ^= 1; } };
+      // four K=16 MMAs over one 64-wide k-block; `tok` / `key` are the shared-memory blocks of the two operands
+      auto group = [&](uint32_t tmem_d, uint32_t tok, uint32_t key, bool first) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t dq = umma_desc_sw128(tok + k4 * 32);
+          const uint64_t dk = umma_desc_sw128(key + k4 * 32);
+          const uint32_t accum = (uint32_t)(!(first && k4 == 0));
+          if (PASS == 1) mq_umma(tmem_d, dq, dk, Cfg::kIdesc, accum);  // D[token, ray]
+          else mq_umma(tmem_d, dk, dq, Cfg::kIdesc, accum);            // D[ray, token]
+        }
+      };
       for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
         for (int b = 0; b < nq; ++b, ++it) {
           const int acc = (int)(it & 1);
@@ -220,20 +312,28 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
           const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
           for (int kb = 0; kb < kMqKBlocks; ++kb) {
             if (b == 0) mbar_wait(&sm.k_full[kb], kphase);
+            const uint32_t kh = smem_u32(sm.kt[kb]);
             mbar_wait(&sm.q_full[stage], qphase);
             tc_fence_after();
-            const uint32_t qa = smem_u32(sm.qs[stage]);
-            const uint32_t ka = smem_u32(sm.kt[kb]);
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t dq = umma_desc_sw128(qa + k4 * 32);
-              const uint64_t dk = umma_desc_sw128(ka + k4 * 32);
-              if (PASS == 1) mq_umma(tmem_d, dq, dk, (uint32_t)((kb | k4) != 0));  // D[token, ray]
-              else mq_umma(tmem_d, dk, dq, (uint32_t)((kb | k4) != 0));            // D[ray, token]
+            const int s_qh = stage;
+            group(tmem_d, smem_u32(sm.qs[s_qh]), kh, kb == 0);                     // Qh . Kh
+            next();
+            if (SPLIT) {
+              mbar_wait(&sm.q_full[stage], qphase);
+              tc_fence_after();
+              group(tmem_d, smem_u32(sm.qs[s_qh]), smem_u32(sm.qs[stage]), false);  // Qh . Kl
+              umma_commit_2sm(&sm.q_empty[s_qh]);
+              umma_commit_2sm(&sm.q_empty[stage]);
+              next();
+              mbar_wait(&sm.q_full[stage], qphase);
+              tc_fence_after();
+              group(tmem_d, smem_u32(sm.qs[stage]), kh, false);                     // Ql . Kh
+              umma_commit_2sm(&sm.q_empty[stage]);
+              next();
+            } else {
+              umma_commit_2sm(&sm.q_empty[s_qh]);                  // token stage free in both CTAs
             }
-            umma_commit_2sm(&sm.q_empty[stage]);                   // token stage free in both CTAs
             if (b == nq - 1) umma_commit_2sm(&sm.k_empty[kb]);     // key slice free once the tile's last query used it
-            if (++stage == kMqStages) { stage = 0; qphase ^= 1; }
           }
           umma_commit_2sm(&sm.tmem_full[acc]);
         }
@@ -248,6 +348,13 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     const int row = quad * 32 + lane;
     int64_t it = 0;
     for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
+      // fused LS: this thread's ray (pass 2: lanes = rays) -- loaded once per tile, used by every query of the batch
+      float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+      const int64_t ray = tile * kMqTileRays + rank * 128 + row;
+      if (fuse_ls && half == 0 && ray < n_rays) {
+        ox = __ldg(rays_ori + ray * 3 + 0); oy = __ldg(rays_ori + ray * 3 + 1); oz = __ldg(rays_ori + ray * 3 + 2);
+        dx = __ldg(rays_dir + ray * 3 + 0); dy = __ldg(rays_dir + ray * 3 + 1); dz = __ldg(rays_dir + ray * 3 + 2);
+      }
       for (int b = 0; b < nq; ++b, ++it) {
         const int acc = (int)(it & 1);
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
@@ -266,7 +373,7 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
             float(&cur)[32] = (c & 1) ? vb : va;
             float(&nxt)[32] = (c & 1) ? va : vb;
             if (c + 1 < 4) tmem_ld32(taddr + (c + 1) * 32, nxt);
-            mq_fold(cur, valid - c * 32, st.x, st.y);
+            mq_fold(cur, valid - c * 32, st.x, st.y, kSc);
             if (c + 1 < 4) tmem_ld_wait(nxt);
           }
           sm.stat[b][half][row] = st;
@@ -283,10 +390,10 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 c4 = cc[j4];
-              s += mq_ex2(cur[j4 * 4 + 0] - c4.x);
-              s1 += mq_ex2(cur[j4 * 4 + 1] - c4.y);
-              s2 += mq_ex2(cur[j4 * 4 + 2] - c4.z);
-              s3 += mq_ex2(cur[j4 * 4 + 3] - c4.w);
+              s += mq_ex2(fmaf(cur[j4 * 4 + 0], kSc, -c4.x));
+              s1 += mq_ex2(fmaf(cur[j4 * 4 + 1], kSc, -c4.y));
+              s2 += mq_ex2(fmaf(cur[j4 * 4 + 2], kSc, -c4.z));
+              s3 += mq_ex2(fmaf(cur[j4 * 4 + 3], kSc, -c4.w));
             }
             if (c + 1 < 4) tmem_ld_wait(nxt);
           }
@@ -294,8 +401,22 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
           if (half == 1) sm.xch[acc][row] = s;
           mq_epi_sync();
           if (half == 0) {
-            const int64_t ray = tile * kMqTileRays + rank * 128 + row;
-            if (ray < n_rays) scores[(int64_t)b * score_stride + ray] = s + sm.xch[acc][row];
+            const float sc = s + sm.xch[acc][row];
+            if (ray < n_rays) scores[(int64_t)b * score_stride + ray] = sc;
+            if (fuse_ls) {
+              // w (I - d d^T), w (I - d d^T) o, w d, w   with w = this ray's score (0 for padding rows)
+              const float w = (ray < n_rays) ? sc : 0.f;
+              const float dd = dx * ox + dy * oy + dz * oz;
+              float v[kMqLs] = {w * (1.f - dx * dx), w * (-dx * dy), w * (-dx * dz), w * (1.f - dy * dy), w * (-dy * dz),
+                                w * (1.f - dz * dz), w * (ox - dx * dd), w * (oy - dy * dd), w * (oz - dz * dd),
+                                w * dx, w * dy, w * dz, w};
+#pragma unroll
+              for (int j = 0; j < kMqLs; ++j) v[j] = warp_sum(v[j]);
+              if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < kMqLs; ++j) sm.ls[b][quad][j] += (double)v[j];
+              }
+            }
           }
         }
         tc_fence_before();
@@ -307,10 +428,12 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
       // merge the two column halves of every (query, token) and write this pair's partial row
       for (int b = 0; b < nq; ++b) {
         const float2 st = sm.stat[b][half][row];
-        if (half == 1) { sm.xch[b & 1][row] = st.x; sm.xch2[b & 1][row] = st.y; }
+        // every MMA has retired (the last accumulator was drained above), so the ring is idle: stage 0 is scratch
+        float(*xch2)[128] = reinterpret_cast<float(*)[128]>(sm.qs[0]);
+        if (half == 1) { sm.xch[b & 1][row] = st.x; xch2[b & 1][row] = st.y; }
         mq_epi_sync();
         if (half == 0) {
-          const float om = sm.xch[b & 1][row], oz = sm.xch2[b & 1][row];
+          const float om = sm.xch[b & 1][row], oz = xch2[b & 1][row];
           const float mn = fmaxf(st.x, om);
           float z = 0.f;
           if (st.x != -INFINITY) z += st.y * mq_ex2(st.x - mn);
@@ -320,6 +443,13 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
           part_m[o] = (mn == -INFINITY) ? -INFINITY : mn * kMqLn2;  // natural-log units
           part_z[o] = z;
         }
+      }
+    } else if (fuse_ls) {
+      mq_epi_sync();  // every half-0 warp has finished its last accumulation
+      if (half == 0 && quad == 0 && lane < kMqLs) {
+        for (int b = 0; b < nq; ++b)
+          ls_part[((int64_t)b * gridDim.x + blockIdx.x) * kMqLs + lane] =
+              ((sm.ls[b][0][lane] + sm.ls[b][1][lane]) + sm.ls[b][2][lane]) + sm.ls[b][3][lane];
       }
     }
   }
@@ -333,35 +463,92 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
   }
 }
 
-int mq_make_map(CUtensorMap* map, const void* base, uint64_t rows) {
-  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, kFeat, (uint64_t)kFeat * 2, "score_tc_mq");
+// sum the per-CTA partial systems in a fixed order: part [nq, n_cta, 13] -> out [nq, 13] (deterministic)
+__global__ void mq_ls_reduce_kernel(const double* __restrict__ part, int n_cta, double* __restrict__ out) {
+  const int b = blockIdx.x, j = threadIdx.x;
+  if (j >= kMqLs) return;
+  double a = 0.0;
+  for (int c = 0; c < n_cta; ++c) a += part[((int64_t)b * n_cta + c) * kMqLs + j];
+  out[b * kMqLs + j] = a;
 }
 
-template <int PASS>
-int mq_launch(const void* kc, int64_t n_rays, const float* q, int nq, int n_img, float* pm, float* pz, const float* m,
-              const float* z, float* scores, int64_t score_stride, void* ws, size_t ws_bytes, cudaStream_t s) {
-  if (nq < 1 || nq > kMqMaxQ) { set_error("score_tc_mq: n_queries must be in [1, %d]", kMqMaxQ); return SIXDGS_EINVAL; }
-  if (ws == nullptr || ws_bytes < (size_t)nq * kMaxTokens * kFeat * sizeof(__nv_bfloat16) + 1024) {
-    set_error("score_tc_mq: workspace too small");
-    return SIXDGS_EWORKSPACE;
+// sys [13] = (R6, q3, wd3, w) scaled by `scale` (1 / n_img: weights = score / n_img, least_squared_loss.py:62-64)
+// -> centre = solve(R, q) (NaN x3 and status bit 0 when det(R) < 1e-7, line_intersection.py:139-142), watch = wd / |wd|
+__global__ void mq_ls_solve_kernel(const double* __restrict__ sys, int n, double scale, float* __restrict__ centre,
+                                   float* __restrict__ watch, int* __restrict__ status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const double* s = sys + (int64_t)b * kMqLs;
+  const double xx = s[0] * scale, xy = s[1] * scale, xz = s[2] * scale, yy = s[3] * scale, yz = s[4] * scale,
+               zz = s[5] * scale, qx = s[6] * scale, qy = s[7] * scale, qz = s[8] * scale;
+  const double c00 = yy * zz - yz * yz, c01 = xz * yz - xy * zz, c02 = xy * yz - xz * yy;
+  const double det = xx * c00 + xy * c01 + xz * c02;
+  int st = 0;
+  // the reference evaluates det(R) in fp32; compare the fp32-rounded value with its literal threshold
+  if (!((float)det >= 1.0e-7f)) {
+    centre[b * 3 + 0] = centre[b * 3 + 1] = centre[b * 3 + 2] = __int_as_float(0x7fc00000);
+    st = 1;
+  } else {
+    const double c11 = xx * zz - xz * xz, c12 = xy * xz - xx * yz, c22 = xx * yy - xy * xy;
+    centre[b * 3 + 0] = (float)((c00 * qx + c01 * qy + c02 * qz) / det);
+    centre[b * 3 + 1] = (float)((c01 * qx + c11 * qy + c12 * qz) / det);
+    centre[b * 3 + 2] = (float)((c02 * qx + c12 * qy + c22 * qz) / det);
   }
+  if (watch) {
+    const double n2 = sqrt(s[9] * s[9] + s[10] * s[10] + s[11] * s[11]);
+    const double inv = n2 > 1e-300 ? 1.0 / n2 : 0.0;
+    watch[b * 3 + 0] = (float)(s[9] * inv); watch[b * 3 + 1] = (float)(s[10] * inv); watch[b * 3 + 2] = (float)(s[11] * inv);
+  }
+  if (status) status[b] = st;
+}
+
+template <bool SPLIT>
+int mq_make_map(CUtensorMap* map, const void* base, uint64_t rows) {
+  constexpr int row = MqCfg<SPLIT>::kRow;
+  return make_tmap_2d(map, SPLIT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, row,
+                      (uint64_t)row * 2, "score_tc_mq");
+}
+
+inline size_t mq_workspace(int nq) { return (size_t)(nq < 1 ? 1 : nq) * kMaxTokens * 2 * kFeat * 2 + 1024; }
+
+template <int PASS, bool SPLIT>
+int mq_launch(const void* kc, int64_t n_rays, const float* q, int nq, int n_img, float* pm, float* pz, const float* m,
+              const float* z, float* scores, int64_t score_stride, const float* ori, const float* dir, double* ls_part,
+              void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (nq < 1 || nq > kMqMaxQ) { set_error("score_tc_mq: n_queries must be in [1, %d]", kMqMaxQ); return SIXDGS_EINVAL; }
+  if (ws == nullptr || ws_bytes < mq_workspace(nq)) { set_error("score_tc_mq: workspace too small"); return SIXDGS_EWORKSPACE; }
   if ((reinterpret_cast<uintptr_t>(kc) & 15) != 0) { set_error("score_tc_mq: key cache must be 16-byte aligned"); return SIXDGS_EINVAL; }
   if (n_rays > (int64_t)INT32_MAX - 1024) { set_error("score_tc_mq: n_rays exceeds the TMA coordinate range"); return SIXDGS_EINVAL; }
-  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+  void* qb = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
   const int64_t nel = (int64_t)nq * kMaxTokens * kFeat;
-  mq_qprep_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(q, n_img, nq, qb);
+  if (SPLIT) mq_qprep_split_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(q, n_img, nq, (__half*)qb);
+  else mq_qprep_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(q, n_img, nq, (__nv_bfloat16*)qb);
   CUtensorMap mk, mq;
   int rc;
-  if ((rc = mq_make_map(&mk, kc, (uint64_t)n_rays))) return rc;
-  if ((rc = mq_make_map(&mq, qb, (uint64_t)nq * kMaxTokens))) return rc;
-  const size_t smem = sizeof(MqSmem) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(score_tc_mq_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if ((rc = mq_make_map<SPLIT>(&mk, kc, (uint64_t)n_rays))) return rc;
+  if ((rc = mq_make_map<SPLIT>(&mq, qb, (uint64_t)nq * kMaxTokens))) return rc;
+  const size_t smem = sizeof(MqSmem<MqCfg<SPLIT>::kStages>) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(score_tc_mq_kernel<PASS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("score_tc_mq attr: %s", cudaGetErrorString(e)); return SIXDGS_ECUDA; }
-  score_tc_mq_kernel<PASS><<<kMqPairs * 2, kMqThreads, smem, s>>>(mk, mq, n_rays, n_img, nq, pm, pz, m, z, scores, score_stride);
+  score_tc_mq_kernel<PASS, SPLIT><<<kMqPairs * 2, kMqThreads, smem, s>>>(mk, mq, n_rays, n_img, nq, pm, pz, m, z, scores,
+                                                                          score_stride, ori, dir, ls_part);
   return check_launch("score_tc_mq");
 }
 
 }  // namespace
+
+// single-query entry points of the exact mode (api.cu dispatches impl 1 + SIXDGS_F16X2 here)
+int score_tc_split_pass1(const void* kc, int64_t n_rays, const float* q, int n_img, float* pm, float* pz, void* ws,
+                         size_t ws_bytes, cudaStream_t s) {
+  return mq_launch<1, true>(kc, n_rays, q, 1, n_img, pm, pz, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, ws,
+                            ws_bytes, s);
+}
+int score_tc_split_pass2(const void* kc, int64_t n_rays, const float* q, int n_img, const float* m, const float* z,
+                         float* scores, void* ws, size_t ws_bytes, cudaStream_t s) {
+  return mq_launch<2, true>(kc, n_rays, q, 1, n_img, nullptr, nullptr, m, z, scores, n_rays, nullptr, nullptr, nullptr, ws,
+                            ws_bytes, s);
+}
+size_t score_tc_split_workspace() { return mq_workspace(1); }
 
 }  // namespace sixdgs
 
@@ -369,26 +556,76 @@ using namespace sixdgs;
 
 extern "C" int sixdgs_score_batch_max(void) { return kMqMaxQ; }
 extern "C" int sixdgs_score_batch_parts(void) { return kMqPairs; }
-extern "C" size_t sixdgs_score_batch_workspace(int n_queries) {
-  return (size_t)(n_queries < 1 ? 1 : n_queries) * kMaxTokens * kFeat * sizeof(__nv_bfloat16) + 1024;
+extern "C" size_t sixdgs_score_batch_workspace(int n_queries) { return mq_workspace(n_queries); }
+extern "C" int sixdgs_ls_partial_rows(void) { return kMqPairs * 2; }
+
+static int mq_check(const void* k_cache, int k_dtype, int64_t n_rays, int n_img) {
+  SIXDGS_REQUIRE(k_cache, "null pointer");
+  SIXDGS_REQUIRE(k_dtype == SIXDGS_BF16 || k_dtype == SIXDGS_F16X2, "the batched path needs a bf16 or f16x2 key cache");
+  SIXDGS_REQUIRE(n_rays >= 1 && n_img >= 1 && n_img <= kMaxTokens, "bad sizes");
+  return SIXDGS_OK;
 }
 
 extern "C" int sixdgs_score_pass1_batch(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries,
                                         int n_img, float* part_m, float* part_z, void* workspace, size_t workspace_bytes,
                                         void* stream) {
-  SIXDGS_REQUIRE(k_cache && q && part_m && part_z, "null pointer");
-  SIXDGS_REQUIRE(k_dtype == SIXDGS_BF16, "the batched path needs a bf16 key cache");
-  SIXDGS_REQUIRE(n_rays >= 1 && n_img >= 1 && n_img <= kMaxTokens, "bad sizes");
-  return mq_launch<1>(k_cache, n_rays, q, n_queries, n_img, part_m, part_z, nullptr, nullptr, nullptr, 0, workspace,
-                      workspace_bytes, (cudaStream_t)stream);
+  SIXDGS_REQUIRE(q && part_m && part_z, "null pointer");
+  int rc = mq_check(k_cache, k_dtype, n_rays, n_img);
+  if (rc) return rc;
+  if (k_dtype == SIXDGS_F16X2)
+    return mq_launch<1, true>(k_cache, n_rays, q, n_queries, n_img, part_m, part_z, nullptr, nullptr, nullptr, 0, nullptr,
+                              nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+  return mq_launch<1, false>(k_cache, n_rays, q, n_queries, n_img, part_m, part_z, nullptr, nullptr, nullptr, 0, nullptr,
+                             nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+static int mq_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries, int n_img,
+                    const float* m, const float* z, float* scores, int64_t score_stride, const float* ori, const float* dir,
+                    double* ls_part, void* workspace, size_t workspace_bytes, void* stream) {
+  SIXDGS_REQUIRE(q && m && z && scores, "null pointer");
+  int rc = mq_check(k_cache, k_dtype, n_rays, n_img);
+  if (rc) return rc;
+  SIXDGS_REQUIRE(score_stride >= n_rays, "score_stride < n_rays");
+  if (k_dtype == SIXDGS_F16X2)
+    return mq_launch<2, true>(k_cache, n_rays, q, n_queries, n_img, nullptr, nullptr, m, z, scores, score_stride, ori, dir,
+                              ls_part, workspace, workspace_bytes, (cudaStream_t)stream);
+  return mq_launch<2, false>(k_cache, n_rays, q, n_queries, n_img, nullptr, nullptr, m, z, scores, score_stride, ori, dir,
+                             ls_part, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int sixdgs_score_pass2_batch(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries,
                                         int n_img, const float* m, const float* z, float* scores, int64_t score_stride,
                                         void* workspace, size_t workspace_bytes, void* stream) {
-  SIXDGS_REQUIRE(k_cache && q && m && z && scores, "null pointer");
-  SIXDGS_REQUIRE(k_dtype == SIXDGS_BF16, "the batched path needs a bf16 key cache");
-  SIXDGS_REQUIRE(n_rays >= 1 && n_img >= 1 && n_img <= kMaxTokens && score_stride >= n_rays, "bad sizes");
-  return mq_launch<2>(k_cache, n_rays, q, n_queries, n_img, nullptr, nullptr, m, z, scores, score_stride, workspace,
-                      workspace_bytes, (cudaStream_t)stream);
+  return mq_pass2(k_cache, k_dtype, n_rays, q, n_queries, n_img, m, z, scores, score_stride, nullptr, nullptr, nullptr,
+                  workspace, workspace_bytes, stream);
+}
+
+extern "C" int sixdgs_score_pass2_batch_ls(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries,
+                                           int n_img, const float* m, const float* z, float* scores, int64_t score_stride,
+                                           const float* rays_ori, const float* rays_dir, double* ls_part, double* ls_sys,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  SIXDGS_REQUIRE(rays_ori && rays_dir && ls_part && ls_sys, "null pointer");
+  int rc = mq_pass2(k_cache, k_dtype, n_rays, q, n_queries, n_img, m, z, scores, score_stride, rays_ori, rays_dir, ls_part,
+                    workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  mq_ls_reduce_kernel<<<n_queries, 32, 0, (cudaStream_t)stream>>>(ls_part, kMqPairs * 2, ls_sys);
+  return check_launch("ls_reduce");
+}
+
+extern "C" int sixdgs_ls_solve(const double* ls_sys, int n, double weight_scale, float* centre, float* watch,
+                               int32_t* status, void* stream) {
+  SIXDGS_REQUIRE(ls_sys && centre, "null pointer");
+  SIXDGS_REQUIRE(n >= 1, "bad size");
+  mq_ls_solve_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(ls_sys, n, weight_scale, centre, watch, status);
+  return check_launch("ls_solve");
+}
+
+extern "C" int sixdgs_split_keys(const float* k_f32, int64_t n, void* k_out, float* absmax, void* stream) {
+  SIXDGS_REQUIRE(k_f32 && k_out, "null pointer");
+  SIXDGS_REQUIRE(n >= 0, "negative size");
+  if (n == 0) return SIXDGS_OK;
+  const int64_t nel = n * kFeat;
+  mq_split_keys_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, (cudaStream_t)stream>>>(k_f32, n, (__half*)k_out,
+                                                                                         (unsigned int*)absmax);
+  return check_launch("split_keys");
 }

@@ -28,7 +28,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from ._lib import BF16, F32
+from ._lib import BF16, F16X2, F32, SixdgsError
 from .camera_up import CameraDirectionPredictor
 from .image_tokens import BackboneWrapper
 
@@ -102,11 +102,14 @@ class MultiHeadAttention(torch.nn.Module):
 
 @dataclass
 class RayKeyCache:
-    """K[n_rays, 384] for one (ray set, weight version); the per-scene state of a query."""
+    """K[n_rays, 384] (fp32 / bf16) or K[n_rays, 768] (f16x2: fp16 hi | lo) for one (ray set, weight version); the
+    per-scene state of a query.  `rays` keeps the three ray tensors alive: the implicit cache of
+    IdentificationModule compares them by identity, so a freed tensor's recycled address can never alias it."""
     keys: torch.Tensor
     n_rays: int
     tag: tuple
     scores: Optional[torch.Tensor] = None  # reusable output buffer
+    rays: Optional[tuple] = None
 
 
 class IdentificationModule(torch.nn.Module):
@@ -128,8 +131,8 @@ class IdentificationModule(torch.nn.Module):
                                             self.backbone_wrapper.img_num_features + 14,
                                             self.backbone_wrapper.img_num_features, 1)
         self.score_impl = score_impl or os.environ.get("SIXDGS_SCORE_IMPL", "simt_fp32")
-        if self.score_impl not in ("simt_fp32", "simt_bf16", "tc_bf16"):
-            raise ValueError("score_impl must be simt_fp32 | simt_bf16 | tc_bf16")
+        if self.score_impl not in ("simt_fp32", "simt_bf16", "tc_bf16", "tc_f16x2"):
+            raise ValueError("score_impl must be simt_fp32 | simt_bf16 | tc_bf16 | tc_f16x2")
         self.attention_map_bytes_limit = attention_map_bytes_limit
         self.features_impl = os.environ.get("SIXDGS_FEATURES_IMPL", "auto")  # auto | simt | tc2 | staged (the last two experimental)
         self._packed_cache = None
@@ -152,15 +155,33 @@ class IdentificationModule(torch.nn.Module):
 
     @property
     def _impl(self) -> int:
-        return ops.SCORE_TC if self.score_impl == "tc_bf16" else ops.SCORE_SIMT
+        return ops.SCORE_TC if self.score_impl in ("tc_bf16", "tc_f16x2") else ops.SCORE_SIMT
 
     @property
     def _k_dtype(self) -> int:
-        return F32 if self.score_impl == "simt_fp32" else BF16
+        return {"simt_fp32": F32, "tc_f16x2": F16X2}.get(self.score_impl, BF16)
+
+    SPLIT_CHUNK = 1 << 20  # rays per fp32 staging chunk of the f16x2 build (1.6 GB of fp32 keys)
 
     @torch.no_grad()
     def build_key_cache(self, rays_ori, rays_dir, rays_rgb) -> RayKeyCache:
         """rays -> PE -> MLP -> k_proj -> K (once per scene / weight update; the reference redoes this per query)."""
+        if self.score_impl == "tc_f16x2":
+            # exact mode: fp32 FMA GEMMs (the TF32 build is only good to 1.5e-3 on the keys), staged through fp32 chunks
+            # and split into fp16 hi | lo rows
+            n = rays_ori.shape[0]
+            keys = torch.empty(n, 2 * 384, dtype=torch.float16, device=rays_ori.device)
+            absmax = torch.zeros(1, dtype=torch.float32, device=rays_ori.device)
+            pw = self.packed_weights()
+            for lo in range(0, n, self.SPLIT_CHUNK):
+                hi = min(n, lo + self.SPLIT_CHUNK)
+                kf, _ = ops.ray_features(rays_ori[lo:hi], rays_dir[lo:hi], rays_rgb[lo:hi], pw, k_dtype=F32,
+                                         impl=ops.FEATURES_SIMT)
+                ops.split_keys(kf, keys[lo:hi], absmax)
+            if n and not float(absmax.item()) < ops.F16_MAX:  # one host read per scene build
+                raise SixdgsError(f"f16x2 key cache: max |16 k| = {float(absmax.item()):.4g} exceeds the fp16 range; "
+                                  "use score_impl='simt_fp32' for keys of this magnitude")
+            return RayKeyCache(keys, n, ())
         # the throughput (bf16-key) modes build the cache with TF32 tensor-core GEMMs; the exact mode keeps fp32 FMA
         impl = ops.FEATURES_TC if (self.score_impl == "tc_bf16" and self.features_impl != "simt") else ops.FEATURES_SIMT
         if impl == ops.FEATURES_TC and self.features_impl in ("tc2", "staged"):  # experimental opt-ins
@@ -168,13 +189,24 @@ class IdentificationModule(torch.nn.Module):
         keys, _ = ops.ray_features(rays_ori, rays_dir, rays_rgb, self.packed_weights(), k_dtype=self._k_dtype, impl=impl)
         return RayKeyCache(keys, keys.shape[0], ())
 
+    def invalidate_key_cache(self):
+        """drop the implicit key cache (call after rewriting a ray buffer in place through raw pointers, which does
+        not bump the tensor version the cache watches)"""
+        self._key_cache = None
+
     def _cache_for(self, rays_ori, rays_dir, rays_rgb) -> RayKeyCache:
-        tag = (rays_ori.data_ptr(), rays_dir.data_ptr(), rays_rgb.data_ptr(), rays_ori.shape[0], rays_ori._version,
-               rays_dir._version, rays_rgb._version, self.score_impl, self._weights_tag())
-        if self._key_cache is None or self._key_cache.tag != tag:
-            self._key_cache = self.build_key_cache(rays_ori, rays_dir, rays_rgb)
-            self._key_cache.tag = tag
-        return self._key_cache
+        """implicit per-module cache: valid while the caller passes the SAME three tensor objects (identity, not
+        address -- the cache holds references, so their storage cannot be freed and recycled under it), unmodified
+        (tensor version counters) and the hot-path weights are unchanged."""
+        tag = (rays_ori._version, rays_dir._version, rays_rgb._version, self.score_impl, self._weights_tag())
+        kc = self._key_cache
+        if (kc is None or kc.rays is None or kc.rays[0] is not rays_ori or kc.rays[1] is not rays_dir
+                or kc.rays[2] is not rays_rgb or kc.tag != tag):
+            self._key_cache = None  # release the old keys before building the new ones
+            kc = self.build_key_cache(rays_ori, rays_dir, rays_rgb)
+            kc.tag, kc.rays = tag, (rays_ori, rays_dir, rays_rgb)
+            self._key_cache = kc
+        return kc
 
     # ------------------------------------------------------------------ query-side
     @torch.no_grad()

@@ -8,7 +8,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, FEAT, MAX_TOKENS, call, dptr, f32c, stream_ptr
+from ._lib import BF16, F16X2, F32, FEAT, MAX_TOKENS, call, dptr, f32c, stream_ptr
 
 SCORE_SIMT = 0
 SCORE_TC = 1
@@ -199,11 +199,30 @@ def project_queries(img_fea: torch.Tensor, pw: Dict[str, torch.Tensor]) -> torch
 
 
 def _kdtype(k: torch.Tensor) -> int:
-    if k.dtype == torch.float32:
+    if k.dtype == torch.float32 and k.shape[-1] == FEAT:
         return F32
-    if k.dtype == torch.bfloat16:
+    if k.dtype == torch.bfloat16 and k.shape[-1] == FEAT:
         return BF16
-    raise _lib.SixdgsError(f"key cache must be float32 or bfloat16, got {k.dtype}")
+    if k.dtype == torch.float16 and k.shape[-1] == 2 * FEAT:
+        return F16X2
+    raise _lib.SixdgsError(f"key cache must be float32 / bfloat16 [n,{FEAT}] or float16 [n,{2 * FEAT}] (f16x2), "
+                           f"got {k.dtype} {tuple(k.shape)}")
+
+
+F16X2_KEY_SCALE = 16.0   # stored f16x2 key = 16 k  (csrc/score_tc_mq.cu)
+F16_MAX = 65504.0
+
+
+def split_keys(k_f32: torch.Tensor, out: Optional[torch.Tensor] = None, absmax: Optional[torch.Tensor] = None):
+    """fp32 keys [n,384] -> exact tensor-core format [n,768] fp16 = [hi | lo] of 16 k.  `absmax` (device float[1],
+    zero-initialised by the caller) accumulates max |16 k| so the caller can check the fp16 range once at the end."""
+    k = f32c(k_f32)
+    n = k.shape[0]
+    if out is None:
+        out = torch.empty(n, 2 * FEAT, dtype=torch.float16, device=k.device)
+    if n:
+        call("sixdgs_split_keys", dptr(k), n, dptr(out, torch.float16), dptr(absmax), stream_ptr())
+    return out
 
 
 _score_ws = {}
@@ -287,18 +306,44 @@ def score_pass1_batch(k_cache: torch.Tensor, q: torch.Tensor, n_img: int = MAX_T
 
 
 def score_pass2_batch(k_cache: torch.Tensor, q: torch.Tensor, m: torch.Tensor, z: torch.Tensor, n_img: int = MAX_TOKENS,
-                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q [B,256,384], m / z [B,256] -> scores [B, n_rays]"""
+                      out: Optional[torch.Tensor] = None, ls_rays=None):
+    """q [B,256,384], m / z [B,256] -> scores [B, n_rays].
+    ls_rays = (rays_ori, rays_dir): additionally accumulate, in the same epilogue, the all-ray weighted least-squares
+    system of least_squared_loss.py:62-64 with weights = scores -> returns (scores, ls_sys [B,13] float64)."""
     _check_batch_q(q)
     nb, n, step = q.shape[0], k_cache.shape[0], score_batch_max()
     scores = out if out is not None else torch.empty(nb, n, dtype=torch.float32, device=q.device)
     ws = _score_batch_workspace(q.device)
+    ls_sys = ls_part = None
+    if ls_rays is not None:
+        rows = int(_lib.load().sixdgs_ls_partial_rows())
+        ls_part = torch.empty(step, rows, 13, dtype=torch.float64, device=q.device)
+        ls_sys = torch.empty(nb, 13, dtype=torch.float64, device=q.device)
     for b0 in range(0, nb, step):
         nq = min(step, nb - b0)
-        call("sixdgs_score_pass2_batch", dptr(k_cache, None), _kdtype(k_cache), n, dptr(q[b0:b0 + nq]), nq, n_img,
-             dptr(m[b0:b0 + nq]), dptr(z[b0:b0 + nq]), dptr(scores[b0:b0 + nq]), scores.stride(0), dptr(ws, torch.uint8),
-             ws.numel(), stream_ptr())
-    return scores
+        if ls_rays is None:
+            call("sixdgs_score_pass2_batch", dptr(k_cache, None), _kdtype(k_cache), n, dptr(q[b0:b0 + nq]), nq, n_img,
+                 dptr(m[b0:b0 + nq]), dptr(z[b0:b0 + nq]), dptr(scores[b0:b0 + nq]), scores.stride(0),
+                 dptr(ws, torch.uint8), ws.numel(), stream_ptr())
+        else:
+            call("sixdgs_score_pass2_batch_ls", dptr(k_cache, None), _kdtype(k_cache), n, dptr(q[b0:b0 + nq]), nq, n_img,
+                 dptr(m[b0:b0 + nq]), dptr(z[b0:b0 + nq]), dptr(scores[b0:b0 + nq]), scores.stride(0),
+                 dptr(f32c(ls_rays[0])), dptr(f32c(ls_rays[1])), dptr(ls_part, torch.float64),
+                 dptr(ls_sys[b0:b0 + nq], torch.float64), dptr(ws, torch.uint8), ws.numel(), stream_ptr())
+    return scores if ls_rays is None else (scores, ls_sys)
+
+
+def ls_solve(ls_sys: torch.Tensor, weight_scale: float = 1.0):
+    """ls_sys [B,13] float64 (summed over shards) -> (centre [B,3], watch [B,3], status [B] int32); the sums are scaled
+    by weight_scale first (1 / n_img: weights = score / n_img, least_squared_loss.py:62-64)."""
+    nb = ls_sys.shape[0]
+    dev = ls_sys.device
+    centre = torch.empty(nb, 3, dtype=torch.float32, device=dev)
+    watch = torch.empty(nb, 3, dtype=torch.float32, device=dev)
+    status = torch.zeros(nb, dtype=torch.int32, device=dev)
+    call("sixdgs_ls_solve", dptr(ls_sys, torch.float64), nb, ctypes.c_double(weight_scale), dptr(centre), dptr(watch),
+         dptr(status, torch.int32), stream_ptr())
+    return centre, watch, status
 
 
 def topk(scores: torch.Tensor, k: int, fused: bool = False):

@@ -46,9 +46,11 @@ def synth_scene(n: int, seed: int = 0, extent: float = 1.0, heavy_tail: bool = F
             "features_rest": f_rest, "sh_degree": sh_degree}
 
 
-def synth_id_weights(seed: int = 0, gain: float = 1.0) -> Dict[str, torch.Tensor]:
+def synth_id_weights(seed: int = 0, gain: float = 1.0, q_gain: float = 1.0) -> Dict[str, torch.Tensor]:
     """Identification-module state dict with U(-b, b), b = gain*sqrt(3/fan_in) weights (unit-ish
-    variance propagation) and small biases; keys match the reference ``id_module.th`` names."""
+    variance propagation) and small biases; keys match the reference ``id_module.th`` names.
+    ``q_gain`` scales ``attention.q_proj`` (weight and bias) afterwards: the random-init logits are nearly flat
+    (std 0.3); q_gain = 20 gives std ~ 6.5, i.e. a peaked, trained-looking softmax over the rays."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for name, shape in ID_MODULE_SHAPES.items():
@@ -58,6 +60,9 @@ def synth_id_weights(seed: int = 0, gain: float = 1.0) -> Dict[str, torch.Tensor
         bound = gain * (3.0 / fan_in) ** 0.5
         sd[name + ".weight"] = (torch.rand(*shape, generator=g) * 2 - 1) * bound
         sd[name + ".bias"] = (torch.rand(shape[0], generator=g) * 2 - 1) * 0.05
+    if q_gain != 1.0:
+        sd["attention.q_proj.weight"] = sd["attention.q_proj.weight"] * q_gain
+        sd["attention.q_proj.bias"] = sd["attention.q_proj.bias"] * q_gain
     return sd
 
 

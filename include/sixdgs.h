@@ -37,6 +37,9 @@ extern "C" {
 
 #define SIXDGS_F32 0
 #define SIXDGS_BF16 1
+/* exact tensor-core key format: a row is [hi(384) | lo(384)] fp16 (1536 B) holding 16*k as hi + lo, hi = fp16(16 k),
+ * lo = fp16(16 k - hi): 22 significant bits.  |k| must stay below 4094 (sixdgs_split_keys reports the maximum). */
+#define SIXDGS_F16X2 2
 
 #define SIXDGS_FEAT 384      /* ray / image embedding width (DINOv2 ViT-S/14), backbone.py:17  */
 #define SIXDGS_MAX_TOKENS 256 /* 16x16 backbone grid, backbone.py:16                            */
@@ -125,7 +128,9 @@ int sixdgs_linear(const float* x, int64_t m, int k, int lda, const float* w, con
  *        tokens >= n_img or with token_valid == 0 get (m, z) = (+inf, +inf) so that pass 2 ignores them
  *        (lets a masked query run on all 256 grid tokens without a host-side compaction / sync).
  * pass2: scores[r] = sum_i exp(L_ir - m_i) / z_i; attn_map (nullable) [n_img, n_rays].
- * impl: 0 = SIMT fp32 (exact path), 1 = tcgen05 bf16 tensor cores (K must be bf16). */
+ * impl: 0 = SIMT fp32 (exact path, fp32 or bf16 K), 1 = tcgen05 tensor cores: bf16 K (throughput mode, one MMA
+ *       term, scores to ~3e-2) or f16x2 K (exact mode: three fp16 MMA terms Qh.Kh + Qh.Kl + Ql.Kh in one fp32
+ *       accumulator, scores to ~1e-5 of the fp32 reference). */
 int sixdgs_score_parts(int impl);
 /* bytes of scratch the chosen impl needs (impl 1: the bf16, pre-scaled copy of q the TMA reads; impl 0: 0) */
 size_t sixdgs_score_workspace(int impl);
@@ -140,13 +145,16 @@ int sixdgs_score_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const f
                        const float* m, const float* z, float* scores, float* attn_map, int impl,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* fp32 keys [n,384] -> SIXDGS_F16X2 rows [n,768]; absmax (nullable, device, zero-initialised by the caller) receives
+ * max |16 k| over the converted rows so the caller can check the fp16 range (must stay < 65504). */
+int sixdgs_split_keys(const float* k_f32, int64_t n, void* k_out, float* absmax, void* stream);
+
 /* ---- a11, several queries per key sweep -------- our_multihead_attention.py:4-12,70-79;
  *                                                  identification_module.py:80-82 (one call per image there)
- * EXPERIMENTAL (not used by any default path yet).  Same mathematics as score_pass1 / score_pass2 with impl 1,
- * for n_queries <= sixdgs_score_batch_max() queries that share the key cache: q[n_queries, 256, 384] fp32,
- * part_m / part_z [n_queries, sixdgs_score_batch_parts(), 256], m / z [n_queries, 256],
- * scores[n_queries, score_stride] (score_stride >= n_rays).  The keys cross HBM once per pass for the whole batch.
- * bf16 key cache only; workspace >= sixdgs_score_batch_workspace(n_queries). */
+ * Same mathematics as score_pass1 / score_pass2 with impl 1, for n_queries <= sixdgs_score_batch_max() queries that
+ * share the key cache: q[n_queries, 256, 384] fp32, part_m / part_z [n_queries, sixdgs_score_batch_parts(), 256],
+ * m / z [n_queries, 256], scores[n_queries, score_stride] (score_stride >= n_rays).  The keys cross HBM once per
+ * pass for the whole batch.  k_dtype SIXDGS_BF16 or SIXDGS_F16X2; workspace >= sixdgs_score_batch_workspace(n_queries). */
 int sixdgs_score_batch_max(void);
 int sixdgs_score_batch_parts(void);
 size_t sixdgs_score_batch_workspace(int n_queries);
@@ -156,6 +164,21 @@ int sixdgs_score_pass1_batch(const void* k_cache, int k_dtype, int64_t n_rays, c
 int sixdgs_score_pass2_batch(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries,
                              int n_img, const float* m, const float* z, float* scores, int64_t score_stride,
                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* pass 2 with the all-ray weighted least-squares system of least_squared_loss.py:47-64 / line_intersection.py:75-154
+ * accumulated in the epilogue (weights = this pass's scores): per query 13 doubles
+ *   R = sum w (I - d d^T) as (xx,xy,xz,yy,yz,zz), q = sum w (I - d d^T) o (3), sum w d (3), sum w
+ * ls_part [n_queries, sixdgs_ls_partial_rows(), 13] = per-CTA partial sums (scratch), ls_sys [n_queries, 13] = their
+ * sum in a fixed order.  Across ray shards the systems simply add: one 13-double all-reduce per query.
+ * sixdgs_ls_solve: centre = solve(R, q) after scaling every sum by weight_scale (1 / n_img in the reference);
+ * NaN x3 and status |= 1 when det(R) < 1e-7; watch (nullable) = normalised sum w d. */
+int sixdgs_ls_partial_rows(void);
+int sixdgs_score_pass2_batch_ls(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries,
+                                int n_img, const float* m, const float* z, float* scores, int64_t score_stride,
+                                const float* rays_ori, const float* rays_dir, double* ls_part, double* ls_sys,
+                                void* workspace, size_t workspace_bytes, void* stream);
+int sixdgs_ls_solve(const double* ls_sys, int n, double weight_scale, float* centre, float* watch, int32_t* status,
+                    void* stream);
 
 /* ---- a12: top-k -------- identification_module.py:131 (torch.topk, sorted descending) -----------
  * workspace >= sixdgs_topk_workspace(n, k).  idx int64, ties broken by lower index first. */

@@ -151,6 +151,35 @@ def gen_id_module(ori, dirs, rgb):
     return idm
 
 
+def gen_id_module_peaked(ori, dirs, rgb, q_gain=20.0):
+    """Same rays / image / weights as gen_id_module but with attention.q_proj scaled by q_gain: the random-init logits
+    are nearly flat (std 0.33), which hides low-precision logit error; x20 gives std ~ 6.5 and per-token effective
+    supports down to ~1 ray, like a trained softmax.  Scores, top-100 and the full pose from the UNMODIFIED reference."""
+    w = synthetic.synth_id_weights(seed=3, q_gain=q_gain)
+    idm = IdentificationModule("dino").eval()
+    missing = idm.load_state_dict(w, strict=False)
+    assert not missing.unexpected_keys, missing.unexpected_keys
+    img = synthetic.synth_image(64, 64, seed=4)
+    mask = torch.ones(64, 64, dtype=torch.bool)
+    with torch.no_grad():
+        tok_pe, _, _ = idm.backbone_wrapper(img, mask)
+        fea = idm.ray_preprocessor(ori, dirs, rgb)
+        idx, vals, scores, up, _ = idm.test_image(img, mask, ori, dirs, rgb, rays_to_output=100)
+        q = torch.nn.functional.linear(tok_pe, w["attention.q_proj.weight"], w["attention.q_proj.bias"])
+        k = torch.nn.functional.linear(fea, w["attention.k_proj.weight"], w["attention.k_proj.bias"])
+        L = (q @ k.t()) / (384 ** 0.5)
+    R = np.eye(3, dtype=np.float32)
+    T = np.array([0.1, -0.2, 2.5], dtype=np.float32)
+    img_u8 = (img * 255).to(torch.uint8).numpy()
+    cam = CameraInfo(uid=0, R=R, T=T, FovY=np.float32(0.9), FovX=np.float32(0.9), image=img_u8, image_path="",
+                     image_name="0", width=64, height=64)
+    results, _, _, _, _ = test_pose_estimation([cam], idm, ori, dirs, rgb, torch.tensor([0.0, 0.0, 1.0]))
+    print(f"peaked: logit std {L.std():.2f}, range {L.max() - L.min():.1f}, score max/min {scores.max():.3e}/{scores.min():.3e}")
+    npz("id_module_peaked.npz", weight_seed=3, q_gain=q_gain, img=img, img_u8=img_u8, scores=scores, topk_idx=idx,
+        topk_vals=vals, up=up, row_max=L.max(-1).values, row_lse=torch.logsumexp(L, -1), logit_std=L.std(),
+        R=R, T=T, pred_c2w=np.array(results[0]["pred_c2w"], dtype=np.float32))
+
+
 def gen_line_intersection():
     g = torch.Generator().manual_seed(21)
     cases = {}
@@ -202,6 +231,10 @@ def gen_pose(idm, ori, dirs, rgb):
 
 
 if __name__ == "__main__":
+    if "--only-peaked" in sys.argv:  # add the peaked-softmax fixture without touching the others (rays from the fixture)
+        g = np.load(os.path.join(OUT, "rays_small.npz"))
+        gen_id_module_peaked(*(torch.from_numpy(g[k]) for k in ("ori", "dirs", "rgb")))
+        sys.exit(0)
     if "--only-heavy" in sys.argv:  # add the heavy-tail fixture without touching the others
         gen_rays()
         sys.exit(0)
@@ -210,6 +243,7 @@ if __name__ == "__main__":
     gen_normals()
     sc, ori, dirs, rgb = gen_rays()
     idm = gen_id_module(ori, dirs, rgb)
+    gen_id_module_peaked(ori, dirs, rgb)
     gen_line_intersection()
     gen_pose(idm, ori, dirs, rgb)
     os.system(f"du -sh {OUT}")
