@@ -56,8 +56,6 @@ _SIGNATURES = {
     "sixdgs_ls_solve": ([c_p, c_i, ctypes.c_double, c_p, c_p, c_p, c_p], c_i),
     "sixdgs_topk_workspace": ([c_i64, c_i], c_sz),
     "sixdgs_topk": ([c_p, c_i64, c_i, c_p, c_p, c_p, c_sz, c_p], c_i),
-    "sixdgs_topk_fused_workspace": ([c_i64, c_i], c_sz),
-    "sixdgs_topk_fused": ([c_p, c_i64, c_i, c_p, c_p, c_p, c_sz, c_p], c_i),
     "sixdgs_line_intersect": ([c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p], c_i),
     "sixdgs_pose_tail": ([c_p, c_p, c_i64, c_p, c_p, c_i, c_p, c_p, c_p, c_p], c_i),
     "sixdgs_gather_candidates": ([c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p], c_i),

@@ -21,7 +21,6 @@ SOURCES = {
     "knn_grid.cu": ["-fmad=false"],
     "features.cu": [],
     "features_tc.cu": [],
-    "features_tc2.cu": [],
     "score_simt.cu": [],
     "score_tc.cu": [],
     "score_tc_mq.cu": [],

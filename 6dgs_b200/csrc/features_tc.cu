@@ -205,7 +205,8 @@ struct __align__(1024) LtStagedSmem {
   uint32_t tmem_base;
 };
 
-// EXPERIMENTAL (impl = 3, opt-in): same GEMM with a shared-memory staged, TMA-store epilogue.
+// impl = 1 (default since round 2; impl = 3 is the direct-store kernel above, kept as the bit-identity reference):
+// same GEMM with a shared-memory staged, TMA-store epilogue.
 template <typename TO>
 __global__ void __launch_bounds__(kLtThreads, 1)
 linear_tc_staged_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,

@@ -1,6 +1,7 @@
 // a12: top-k of the ray scores (reference identification_module.py:131, torch.topk sorted descending).
 // MSB-first 8-bit radix select on order-preserving float keys: 4 histogram sweeps fix the exact
-// k-th key, one gather sweep collects everything above it plus the ties, one CTA sorts the k winners.
+// k-th key, one gather sweep collects everything above it plus the ties, one CTA sorts the k winners
+// (ties by lowest index first, deterministically -- also when there are more ties than the tie table holds).
 // All control state lives in the caller's workspace, so the whole thing is stream-ordered with no
 // host round trip (the reference's torch.topk is also a single device op).
 #include "common.cuh"
@@ -16,7 +17,8 @@ struct TopkState {
 };
 
 __device__ __forceinline__ uint32_t f2key(float f) {
-  const uint32_t b = __float_as_uint(f);
+  uint32_t b = __float_as_uint(f);
+  if (b == 0x80000000u) b = 0u;  // -0.0 == +0.0 (torch.topk compares values, not bit patterns)
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 __device__ __forceinline__ float key2f(uint32_t k) {
@@ -43,19 +45,27 @@ __global__ void __launch_bounds__(256) topk_hist_kernel(const float* __restrict_
   if (h[threadIdx.x]) atomicAdd(&st->hist[pass][threadIdx.x], h[threadIdx.x]);
 }
 
-__global__ void topk_select_kernel(TopkState* st, int pass) {
-  if (threadIdx.x != 0) return;
+// pick the digit of the k-th key from this pass's histogram: the largest d with  #(digit >= d) >= k_rem  (0 if none).
+// One 256-thread CTA, suffix sums in shared memory (the round-1 single-thread walk cost ~10 us per pass).
+__global__ void __launch_bounds__(256) topk_select_kernel(TopkState* st, int pass) {
+  __shared__ uint32_t suf[257];
+  const int t = threadIdx.x;
   const int shift = 24 - 8 * pass;
-  uint32_t k_rem = st->k_rem, above = 0;
-  int d = 255;
-  for (; d > 0; --d) {
-    const uint32_t c = st->hist[pass][d];
-    if (above + c >= k_rem) break;
-    above += c;
+  const uint32_t k_rem = st->k_rem;
+  suf[t] = st->hist[pass][t];
+  if (t == 0) suf[256] = 0;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    const uint32_t v = (t + off < 256) ? suf[t + off] : 0u;
+    __syncthreads();
+    suf[t] += v;
+    __syncthreads();
   }
-  st->prefix |= ((uint32_t)d) << shift;
-  st->mask |= 0xffu << shift;
-  st->k_rem = k_rem - above;
+  if ((t == 0 || suf[t] >= k_rem) && suf[t + 1] < k_rem) {  // exactly one thread (suf is non-increasing)
+    st->prefix |= ((uint32_t)t) << shift;
+    st->mask |= 0xffu << shift;
+    st->k_rem = k_rem - suf[t + 1];
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -124,67 +134,33 @@ topk_final_kernel(TopkState* st, const uint32_t* __restrict__ ckey, const int64_
   if (t < k) { vals[t] = key2f(skey[t]); idx[t] = sidx[t]; }
 }
 
-// EXPERIMENTAL variant (sixdgs_topk_fused): the digit selection runs in the LAST histogram CTA to finish (atomic
-// ticket) with a 256-thread suffix scan, instead of a single-thread kernel per pass: 7 launches instead of 11 and no
-// 10 us serial bin walks -- matters when the shard is small (8 GPUs: 3.6 M scores, the four sweeps take ~4 us each).
-struct TopkStateFused {
-  TopkState st;
-  uint32_t ticket[4];
-};
-
-__global__ void topk_init_fused_kernel(TopkStateFused* sf, int k) {
-  const int t = threadIdx.x;
-  for (int i = t; i < 4 * 256; i += blockDim.x) (&sf->st.hist[0][0])[i] = 0;
-  if (t < 4) sf->ticket[t] = 0;
-  if (t == 0) { sf->st.prefix = 0; sf->st.mask = 0; sf->st.k_rem = (uint32_t)k; sf->st.n_gt = 0; sf->st.n_eq = 0; }
-}
-
-__global__ void __launch_bounds__(256)
-topk_hist_select_kernel(const float* __restrict__ x, int64_t n, TopkStateFused* sf, int pass) {
-  __shared__ uint32_t h[256];
-  __shared__ uint32_t wsum[8];
-  __shared__ bool last;
-  TopkState* st = &sf->st;
-  const int t = threadIdx.x;
-  h[t] = 0;
-  __syncthreads();
-  const uint32_t prefix = st->prefix, mask = st->mask;
-  const int shift = 24 - 8 * pass;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + t; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t u = f2key(x[i]);
-    if ((u & mask) == prefix) atomicAdd(&h[(u >> shift) & 0xffu], 1u);
+// Ties at the k-th key beyond kTieCap: the gather above records ties in atomic arrival order, which is only harmless
+// while ALL of them fit the table (they are sorted by index afterwards).  With more than kTieCap equal keys (many
+// zero / underflowed scores, an all-masked query) the survivors would depend on scheduling.  This single-CTA kernel
+// exits at once unless that happened; otherwise it rescans the scores in index order and rewrites the table with the
+// lowest-index ties -- deterministic, and identical on every rank.  It stops as soon as `need` ties are found.
+__global__ void __launch_bounds__(1024)
+topk_ties_kernel(const float* __restrict__ x, int64_t n, TopkState* st, int64_t* __restrict__ tie_idx, int k) {
+  if (st->n_eq <= (uint32_t)kTieCap) return;
+  __shared__ uint32_t wsum[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint32_t T = st->prefix;
+  const uint32_t need = (uint32_t)k - min(st->n_gt, (uint32_t)k);
+  uint32_t found = 0;
+  for (int64_t base = 0; base < n && found < need; base += 1024) {
+    const int64_t i = base + t;
+    const bool tie = i < n && f2key(x[i]) == T;
+    const uint32_t bal = __ballot_sync(0xffffffffu, tie);
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (int j = 0; j < 32; ++j) { const uint32_t c = wsum[j]; if (j < w) before += c; total += c; }
+    const uint32_t pos = found + before + __popc(bal & ((1u << lane) - 1u));
+    if (tie && pos < (uint32_t)kTieCap) tie_idx[pos] = i;
+    found += total;
+    __syncthreads();
   }
-  __syncthreads();
-  if (h[t]) atomicAdd(&st->hist[pass][t], h[t]);
-  __threadfence();
-  __syncthreads();
-  if (t == 0) last = atomicAdd(&sf->ticket[pass], 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  // inclusive suffix sums S[d] = sum_{j >= d} hist[j]; the digit is the largest d with S[d] >= k_rem
-  const uint32_t c = atomicAdd(&st->hist[pass][t], 0u);  // L2 read of the completed histogram
-  const int lane = t & 31, w = t >> 5;
-  uint32_t v = c;  // suffix scan inside the warp (towards higher lanes)
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t up = __shfl_down_sync(0xffffffffu, v, o);
-    if (lane + o < 32) v += up;
-  }
-  if (lane == 0) wsum[w] = v;
-  __syncthreads();
-  uint32_t higher = 0;  // counts in the warps above this one
-  for (int j = w + 1; j < 8; ++j) higher += wsum[j];
-  const uint32_t S = v + higher;      // elements with digit >= t
-  const uint32_t above = S - c;       // elements with digit >  t
-  const uint32_t k_rem = st->k_rem;
-  __syncthreads();                    // everyone has read k_rem before it is rewritten
-  const bool hit = (S >= k_rem && above < k_rem) || (t == 0 && S < k_rem);  // digit 0 also catches "fewer than k left"
-  if (hit) {
-    st->prefix = prefix | ((uint32_t)t << shift);
-    st->mask = mask | (0xffu << shift);
-    st->k_rem = k_rem - above;
-  }
+  if (t == 0) st->n_eq = min(found, (uint32_t)kTieCap);  // `found` is the same in every thread
 }
 
 // n <= 4096 (e.g. the cross-rank candidate table, world * k rows): one CTA, one launch -- load everything,
@@ -229,38 +205,6 @@ extern "C" size_t sixdgs_topk_workspace(int64_t n, int k) {
   return sizeof(TopkState) + (size_t)k * (sizeof(uint32_t) + sizeof(int64_t)) + kTieCap * sizeof(int64_t) + 64;
 }
 
-extern "C" size_t sixdgs_topk_fused_workspace(int64_t n, int k) { return sixdgs_topk_workspace(n, k) + 64; }
-
-// EXPERIMENTAL: same contract and results as sixdgs_topk, 7 launches instead of 11 (selection fused into the sweeps)
-extern "C" int sixdgs_topk_fused(const float* scores, int64_t n, int k, float* vals, int64_t* idx, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
-  SIXDGS_REQUIRE(scores && vals && idx && workspace, "null pointer");
-  SIXDGS_REQUIRE(k >= 1 && k <= kTopkMaxK, "k must be in [1, 1024]");
-  SIXDGS_REQUIRE(n >= k, "selected index k out of range");
-  if (workspace_bytes < sixdgs_topk_fused_workspace(n, k)) {
-    set_error("topk_fused: workspace too small");
-    return SIXDGS_EWORKSPACE;
-  }
-  cudaStream_t s = (cudaStream_t)stream;
-  if (n <= kSmallN) {
-    topk_small_kernel<<<1, 1024, 0, s>>>(scores, (int)n, k, vals, idx);
-    return check_launch("topk_small");
-  }
-  unsigned char* w = (unsigned char*)workspace;
-  TopkStateFused* sf = (TopkStateFused*)w;
-  w += sizeof(TopkStateFused) + (64 - sizeof(TopkStateFused) % 64) % 64;
-  int64_t* cidx = (int64_t*)w; w += (size_t)k * sizeof(int64_t);
-  int64_t* tie = (int64_t*)w; w += kTieCap * sizeof(int64_t);
-  uint32_t* ckey = (uint32_t*)w;
-  const int64_t want = (n + 256 * 8 - 1) / (256 * 8);
-  const unsigned grid = (unsigned)(want < kNumSMs * 8 ? (want > 0 ? want : 1) : kNumSMs * 8);
-  topk_init_fused_kernel<<<1, 256, 0, s>>>(sf, k);
-  for (int p = 0; p < 4; ++p) topk_hist_select_kernel<<<grid, 256, 0, s>>>(scores, n, sf, p);
-  topk_gather_kernel<<<grid, 256, 0, s>>>(scores, n, &sf->st, ckey, cidx, tie, k);
-  topk_final_kernel<<<1, 1024, 0, s>>>(&sf->st, ckey, cidx, tie, k, vals, idx);
-  return check_launch("topk_fused");
-}
-
 extern "C" int sixdgs_topk(const float* scores, int64_t n, int k, float* vals, int64_t* idx, void* workspace,
                            size_t workspace_bytes, void* stream) {
   SIXDGS_REQUIRE(scores && vals && idx && workspace, "null pointer");
@@ -286,9 +230,10 @@ extern "C" int sixdgs_topk(const float* scores, int64_t n, int k, float* vals, i
   topk_init_kernel<<<1, 256, 0, s>>>(st, k);
   for (int p = 0; p < 4; ++p) {
     topk_hist_kernel<<<grid, 256, 0, s>>>(scores, n, st, p);
-    topk_select_kernel<<<1, 32, 0, s>>>(st, p);
+    topk_select_kernel<<<1, 256, 0, s>>>(st, p);
   }
   topk_gather_kernel<<<grid, 256, 0, s>>>(scores, n, st, ckey, cidx, tie, k);
+  topk_ties_kernel<<<1, 1024, 0, s>>>(scores, n, st, tie, k);  // no-op unless more than kTieCap ties at the k-th key
   topk_final_kernel<<<1, 1024, 0, s>>>(st, ckey, cidx, tie, k, vals, idx);
   return check_launch("topk");
 }

@@ -134,7 +134,7 @@ class IdentificationModule(torch.nn.Module):
         if self.score_impl not in ("simt_fp32", "simt_bf16", "tc_bf16", "tc_f16x2"):
             raise ValueError("score_impl must be simt_fp32 | simt_bf16 | tc_bf16 | tc_f16x2")
         self.attention_map_bytes_limit = attention_map_bytes_limit
-        self.features_impl = os.environ.get("SIXDGS_FEATURES_IMPL", "auto")  # auto | simt | tc2 | staged (the last two experimental)
+        self.features_impl = os.environ.get("SIXDGS_FEATURES_IMPL", "auto")  # auto | simt | direct (TF32, direct-store epilogue)
         self._packed_cache = None
         self._key_cache: Optional[RayKeyCache] = None
 
@@ -184,8 +184,8 @@ class IdentificationModule(torch.nn.Module):
             return RayKeyCache(keys, n, ())
         # the throughput (bf16-key) modes build the cache with TF32 tensor-core GEMMs; the exact mode keeps fp32 FMA
         impl = ops.FEATURES_TC if (self.score_impl == "tc_bf16" and self.features_impl != "simt") else ops.FEATURES_SIMT
-        if impl == ops.FEATURES_TC and self.features_impl in ("tc2", "staged"):  # experimental opt-ins
-            impl = ops.FEATURES_TC2 if self.features_impl == "tc2" else ops.FEATURES_TC_STAGED
+        if impl == ops.FEATURES_TC and self.features_impl == "direct":
+            impl = ops.FEATURES_TC_DIRECT
         keys, _ = ops.ray_features(rays_ori, rays_dir, rays_rgb, self.packed_weights(), k_dtype=self._k_dtype, impl=impl)
         return RayKeyCache(keys, keys.shape[0], ())
 

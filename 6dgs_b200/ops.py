@@ -153,9 +153,8 @@ def pack_ray_mlp_weights(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch
 
 
 FEATURES_SIMT = 0  # fp32 FMA GEMMs (exact)
-FEATURES_TC = 1    # TF32 tcgen05 GEMMs
-FEATURES_TC2 = 2   # EXPERIMENTAL: CTA-pair full-width TF32 tiles (features_tc2.cu); correct, not faster (round 1)
-FEATURES_TC_STAGED = 3  # EXPERIMENTAL: 1-CTA kernel with a shared-memory staged TMA-store epilogue
+FEATURES_TC = 1    # TF32 tcgen05 GEMMs, shared-memory staged TMA-store epilogue
+FEATURES_TC_DIRECT = 3  # same GEMMs, direct-store epilogue (bit-identical, 8 % slower; the comparison kernel)
 
 
 def ray_features(ori, dirs, rgb, pw: Dict[str, torch.Tensor], k_dtype: Optional[int] = F32, want_features: bool = False,
@@ -172,7 +171,7 @@ def ray_features(ori, dirs, rgb, pw: Dict[str, torch.Tensor], k_dtype: Optional[
         return k_out, feat
     wsz = int(_lib.load().sixdgs_ray_features_workspace(n))
     ws = torch.empty(wsz, dtype=torch.uint8, device=dev)
-    sfx = "_tf32" if impl in (FEATURES_TC, FEATURES_TC2, FEATURES_TC_STAGED) else ""
+    sfx = "_tf32" if impl in (FEATURES_TC, FEATURES_TC_DIRECT) else ""
     call("sixdgs_ray_features", dptr(ori), dptr(dirs), dptr(rgb), n, dptr(pw["w1p" + sfx]), dptr(pw["b1"]),
          dptr(pw["w2" + sfx]), dptr(pw["b2"]), dptr(pw["w3p" + sfx]), dptr(pw["b3"]), dptr(pw["w4" + sfx]), dptr(pw["b4"]),
          dptr(pw["wk" + sfx]) if project else None, dptr(pw["bk"]) if project else None,
@@ -346,15 +345,13 @@ def ls_solve(ls_sys: torch.Tensor, weight_scale: float = 1.0):
     return centre, watch, status
 
 
-def topk(scores: torch.Tensor, k: int, fused: bool = False):
-    """fused=True: EXPERIMENTAL variant with the digit selection inside the histogram sweeps (same results)"""
+def topk(scores: torch.Tensor, k: int):
     n = scores.shape[0]
     vals = torch.empty(k, dtype=torch.float32, device=scores.device)
     idx = torch.empty(k, dtype=torch.int64, device=scores.device)
-    fn = "sixdgs_topk_fused" if fused else "sixdgs_topk"
-    wsz = int(getattr(_lib.load(), fn + "_workspace")(n, k))
+    wsz = int(_lib.load().sixdgs_topk_workspace(n, k))
     ws = torch.empty(wsz, dtype=torch.uint8, device=scores.device)
-    call(fn, dptr(scores), n, k, dptr(vals), dptr(idx, torch.int64), dptr(ws, torch.uint8), wsz, stream_ptr())
+    call("sixdgs_topk", dptr(scores), n, k, dptr(vals), dptr(idx, torch.int64), dptr(ws, torch.uint8), wsz, stream_ptr())
     return vals, idx
 
 

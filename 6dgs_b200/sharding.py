@@ -2,7 +2,7 @@
 
 Each rank owns a contiguous block of the selected ellipsoids, hence its own rays and its own slice
 of the key cache; image tokens, weights and the camera-up head are replicated (they are tiny).
-Only two things couple the shards, each one small all-gather per query:
+Only two things couple the shards, each one small all-gather per batch of queries:
   1. softmax statistics: every rank's partial (max, sum-exp) rows -> log-sum-exp merge -> (m, z)[256]
   2. candidates: every rank's local top-k (score, origin, direction) -> global top-k -> pose tail,
      computed redundantly on every rank (exactly the reference's top-100 semantics, test.py:85-198).
@@ -23,9 +23,8 @@ from . import _lib, ops
 class CudaBackend:
     """The product backend: every call lands in libsixdgs.so."""
 
-    def __init__(self, idm, fused_topk: bool = False):
+    def __init__(self, idm):
         self.idm = idm
-        self.fused_topk = bool(fused_topk)  # EXPERIMENTAL: sixdgs_topk_fused (7 launches instead of 11)
         self.impl = idm._impl
         self.parts = int(_lib.load().sixdgs_score_parts(self.impl))
 
@@ -55,7 +54,7 @@ class CudaBackend:
     def pass2(self, keys, q, m, z, out):
         return ops.score_pass2(keys, q, m, z, self.impl, out=out)[0]
 
-    # several queries per key sweep (EXPERIMENTAL; ShardedPoseEstimator(multi_query=True), bf16 key cache only)
+    # several queries per key sweep (ShardedPoseEstimator(multi_query=True); bf16 or f16x2 key cache)
     def pass1_batch(self, keys, q):
         return ops.score_pass1_batch(keys, q)
 
@@ -63,7 +62,7 @@ class CudaBackend:
         return ops.score_pass2_batch(keys, q, m, z, out=out)
 
     def topk(self, scores, k):
-        return ops.topk(scores, k, fused=self.fused_topk)
+        return ops.topk(scores, k)
 
     def camera_up(self, grid):
         """[B,384,16,16] -> unit up vectors [B,3]"""
@@ -89,17 +88,20 @@ class ShardedPoseEstimator:
     "replicated".  With ``query_batch(..., local=True)`` the caller passes just this rank's images, so only
     those cross PCIe.
 
-    ``multi_query`` (EXPERIMENTAL, tensor-core path only): score the whole batch in one sweep over the key cache per
-    pass (csrc/score_tc_mq.cu) instead of one sweep per query."""
+    ``multi_query`` (tensor-core path only; default: on for it): score the whole batch in one sweep over the key cache
+    per pass (csrc/score_tc_mq.cu) instead of one sweep per query -- bit-identical scores, the keys cross HBM once per
+    pass per batch."""
 
     def __init__(self, idm, rays_ori: torch.Tensor, rays_dir: torch.Tensor, cache, rank: int = 0, world: int = 1,
-                 backend=None, group=None, front_end: str = "replicated", multi_query: bool = False):
+                 backend=None, group=None, front_end: str = "replicated", multi_query: Optional[bool] = None):
         if front_end not in ("replicated", "sharded"):
             raise ValueError(f"front_end must be 'replicated' or 'sharded', got {front_end!r}")
         self.backend = backend or CudaBackend(idm)
         self.ori, self.dirs, self.cache = rays_ori, rays_dir, cache
         self.rank, self.world, self.group = rank, world, group
         self.front_end = front_end
+        if multi_query is None:
+            multi_query = getattr(self.backend, "impl", ops.SCORE_SIMT) == ops.SCORE_TC
         self.multi_query = bool(multi_query)
         if self.multi_query and getattr(self.backend, "impl", ops.SCORE_TC) != ops.SCORE_TC:
             raise ValueError("multi_query needs the tensor-core score path (score_impl='tc_bf16')")
@@ -108,10 +110,10 @@ class ShardedPoseEstimator:
         if cache.scores is None:
             cache.scores = torch.empty(cache.n_rays, dtype=torch.float32, device=rays_ori.device)
         # libsixdgs launches per query: pass 1 + merge + pass 2 (3, +2 q-prep on the tensor-core path), radix top-k
-        # (11; 1 when the shard has <= 4096 rays), pose tail 1, and when sharded candidate pack 1 + global top-k 1.
+        # (12; 1 when the shard has <= 4096 rays), pose tail 1, and when sharded candidate pack 1 + global top-k 1.
         # The q projection is one launch per batch (launches_per_batch).
         tc = 2 if getattr(self.backend, "impl", 0) == ops.SCORE_TC else 0
-        radix = 7 if getattr(self.backend, "fused_topk", False) else 11
+        radix = 12  # init, 4 x (histogram, select), gather, tie fix-up, final
         self.launches_per_query = 3 + tc + (radix if cache.n_rays > 4096 else 1) + 1 + (2 if world > 1 else 0)
         self.launches_per_batch = 1
         if self.multi_query:  # per query only the merge remains; per batch (of <= 8) q-prep + kernel for each pass
@@ -162,7 +164,8 @@ class ShardedPoseEstimator:
             pm = torch.cat([p[0] for p in parts], 0)  # [B * parts, 256]
             pz = torch.cat([p[1] for p in parts], 0)
             rows = parts[0][0].shape[0]
-        return {"q": q, "valid": valid, "up": up, "pm": pm, "pz": pz, "n_img": n_img, "nb": nb, "rows": rows}
+        # one buffer for both statistics, [2 * B * rows, 256] = pm rows then pz rows: ONE all-gather per batch
+        return {"q": q, "valid": valid, "up": up, "pmz": torch.cat((pm, pz), 0), "n_img": n_img, "nb": nb, "rows": rows}
 
     def _stage1(self, imgs, masks):
         """images -> tokens -> q, camera up, and this shard's partial softmax rows for every query of the batch"""
@@ -205,12 +208,14 @@ class ShardedPoseEstimator:
         bl = imgs.shape[0] // self.world
         return imgs[self.rank * bl:(self.rank + 1) * bl], masks[self.rank * bl:(self.rank + 1) * bl]
 
-    def _stage2(self, pm, pz, st, k):
+    def _stage2(self, pmz, st, k):
         """merged statistics -> scores -> local top-k per query (+ packed candidates when sharded).
-        pm/pz are [world * B * rows, 256] (rank-major); query i owns rows [r*B*rows + i*rows, +rows) of every rank r."""
+        pmz is [world * 2 * B * rows, 256]: per rank the pm rows of the batch, then its pz rows; query i owns rows
+        [r*2*B*rows + i*rows, +rows) (pm) and the same shifted by B*rows (pz) of every rank r."""
         b = self.backend
         nb, rows = st["nb"], st["rows"]
-        groups = pm.shape[0] // (nb * rows)  # == world
+        groups = pmz.shape[0] // (2 * nb * rows)  # == world
+        pm, pz = pmz, pmz[nb * rows:]
         k_local = min(k, self.cache.n_rays)
         vals, idxs = [], []
         cand = None
@@ -219,7 +224,7 @@ class ShardedPoseEstimator:
         def merged(i):
             # query i's rows: [rank g][query i][0..rows) -> group stride nb*rows, first row i*rows (no copies)
             return b.merge(pm, pz, st["n_img"], st["valid"][i] if st["valid"] is not None else None,
-                           rows=rows, groups=groups, group_stride=nb * rows, first_row=i * rows)
+                           rows=rows, groups=groups, group_stride=2 * nb * rows, first_row=i * rows)
 
         scores_b = None
         if self.multi_query:
@@ -260,10 +265,10 @@ class ShardedPoseEstimator:
             st = self._pass1_all(*self._unpack_front(rec, q.shape[1], q.shape[2]))
         else:
             st = self._stage1(imgs, masks)
-        pm, pz = st["pm"], st["pz"]
+        pmz = st["pmz"]
         if self.world > 1:
-            pm, pz = self._all_gather(pm), self._all_gather(pz)
-        vals, idxs, cand = self._stage2(pm, pz, st, k)
+            pmz = self._all_gather(pmz)
+        vals, idxs, cand = self._stage2(pmz, st, k)
         if self.world == 1:
             outs = [self.backend.pose_tail(self.ori, self.dirs, idxs[i], vals[i], st["up"][i]) for i in range(st["nb"])]
             return torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
@@ -308,10 +313,9 @@ class ShardedPoseEstimator:
                 else:
                     with torch.cuda.graph(g1):
                         g["st"] = self._stage1(g["img"], g["mask"])
-                g["pm_all"] = self._all_gather(g["st"]["pm"])
-                g["pz_all"] = self._all_gather(g["st"]["pz"])
+                g["pmz_all"] = self._all_gather(g["st"]["pmz"])
                 with torch.cuda.graph(g2):
-                    _, _, g["cand"] = self._stage2(g["pm_all"], g["pz_all"], g["st"], k)
+                    _, _, g["cand"] = self._stage2(g["pmz_all"], g["st"], k)
                 g["allc"] = self._all_gather(g["cand"])
                 with torch.cuda.graph(g3):
                     g["out"] = self._stage3(g["allc"], g["st"]["up"], k, g["st"]["nb"])
@@ -341,8 +345,7 @@ class ShardedPoseEstimator:
                 g["front_graph"].replay()
                 self._all_gather(g["rec"], g["rec_all"])
             g["graphs"][0].replay()
-            self._all_gather(g["st"]["pm"], g["pm_all"])
-            self._all_gather(g["st"]["pz"], g["pz_all"])
+            self._all_gather(g["st"]["pmz"], g["pmz_all"])
             g["graphs"][1].replay()
             self._all_gather(g["cand"], g["allc"])
             g["graphs"][2].replay()

@@ -104,8 +104,8 @@ int sixdgs_exclusive_scan(const int32_t* in, int64_t n, int64_t* out, void* stre
  *   w4 [384,512]  = mlp2.2.weight                     b4[384]
  *   wk [384,384]  = attention.k_proj.weight (nullable: skip projection, emit features) bk[384]
  * k_out[n,384] in k_dtype (SIXDGS_F32 | SIXDGS_BF16); feat_out (nullable) = pre-projection features.
- * impl: 0 = fp32 FMA GEMMs (exact path), 1 = TF32 tcgen05 GEMMs (TMA + TMEM; throughput path),
- *       2 = experimental CTA-pair TF32 GEMMs with full-width tiles (opt-in).
+ * impl: 0 = fp32 FMA GEMMs (exact path), 1 = TF32 tcgen05 GEMMs (TMA + TMEM, staged TMA-store epilogue; throughput
+ *       path), 3 = the same GEMMs with a direct-store epilogue (bit-identical; kept as the comparison kernel).
  * workspace >= sixdgs_ray_features_workspace(n) bytes. */
 size_t sixdgs_ray_features_workspace(int64_t n);
 int sixdgs_ray_features(const float* ori, const float* dir, const float* rgb, int64_t n,
@@ -185,10 +185,6 @@ int sixdgs_ls_solve(const double* ls_sys, int n, double weight_scale, float* cen
 size_t sixdgs_topk_workspace(int64_t n, int k);
 int sixdgs_topk(const float* scores, int64_t n, int k, float* vals, int64_t* idx, void* workspace,
                 size_t workspace_bytes, void* stream);
-/* EXPERIMENTAL: same contract and results, digit selection fused into the histogram sweeps (7 launches, not 11) */
-size_t sixdgs_topk_fused_workspace(int64_t n, int k);
-int sixdgs_topk_fused(const float* scores, int64_t n, int k, float* vals, int64_t* idx, void* workspace,
-                      size_t workspace_bytes, void* stream);
 
 /* ---- a13: least-squares line intersection -------- line_intersection.py:75-154 ------------------
  * R = sum w (I - d d^T), q = sum w (I - d d^T) o, centre = solve(R, q); NaN x3 and *status |= 1 when

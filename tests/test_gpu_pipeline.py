@@ -1,40 +1,16 @@
-"""Opt-in checks for code that is built but not on any default path yet (run on a B200 with
-SIXDGS_EXPERIMENTAL=1 python -m pytest tests/test_experimental.py).  They are skipped in the driver's CPU and GPU
-test runs on purpose: an experimental kernel must never be able to break the validated suite."""
-import os
-
+"""GPU tests of the batch / multi-GPU pipeline pieces that were written without a GPU at the end of round 1 and
+validated on a B200 at the start of round 2 (profiles/validate_experimental_r2.log): the multi-query score kernel, the
+sharded image front end, the staged TMA-store GEMM epilogue, the heavy-tailed ray-generation fixture; plus the
+deterministic tie handling of the top-k and the key-cache identity rule."""
 import pytest
 import torch
 
-run = os.environ.get("SIXDGS_EXPERIMENTAL") == "1" and torch.cuda.is_available()
-pytestmark = pytest.mark.skipif(not run, reason="set SIXDGS_EXPERIMENTAL=1 on a GPU box")
-
-
-def test_cta_pair_tf32_gemm_matches_the_one_cta_kernel(sx, synthetic):
-    """features_tc2.cu (CTA pairs, full-width tiles) vs features_tc.cu (validated) vs the fp32 build"""
-    dev = "cuda"
-    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone())
-    idm.load_state_dict(synthetic.synth_id_weights(seed=3), strict=False)
-    pw = idm.to(dev).packed_weights()
-    gen = torch.Generator().manual_seed(3)
-    for n in (1, 255, 256, 257, 200_000):
-        ori = (torch.randn(n, 3, generator=gen) * 3).to(dev)
-        dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1).to(dev)
-        rgb = torch.rand(n, 3, generator=gen).to(dev)
-        k1, f1 = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.F32, want_features=True, impl=sx.ops.FEATURES_TC)
-        k2, f2 = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.F32, want_features=True, impl=sx.ops.FEATURES_TC2)
-        k0, _ = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.F32, impl=sx.ops.FEATURES_SIMT)
-        torch.cuda.synchronize()
-        scale = k0.abs().max().item()
-        assert (k2 - k1).abs().max().item() <= 2e-4 * scale, n   # same TF32 products, different accumulation order
-        assert (k2 - k0).abs().max().item() <= 1.5e-3 * scale, n
-        kb, _ = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=sx._lib.BF16, impl=sx.ops.FEATURES_TC2)
-        assert (kb.float() - k0).abs().max().item() <= 4e-3 * scale
+pytestmark = pytest.mark.gpu
 
 
 def test_staged_tma_store_epilogue_matches_the_direct_store_kernel(sx, synthetic):
-    """features_tc.cu: linear_tc_staged_kernel (smem-staged TMA tensor stores) must be bit-identical to
-    linear_tc_kernel (same MMAs, same epilogue math; only the way the tile reaches HBM differs)"""
+    """features_tc.cu: linear_tc_staged_kernel (smem-staged TMA tensor stores, the default TF32 build) must be
+    bit-identical to linear_tc_kernel (same MMAs, same epilogue math; only the way the tile reaches HBM differs)"""
     dev = "cuda"
     idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone())
     idm.load_state_dict(synthetic.synth_id_weights(seed=3), strict=False)
@@ -45,8 +21,8 @@ def test_staged_tma_store_epilogue_matches_the_direct_store_kernel(sx, synthetic
         dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1).to(dev)
         rgb = torch.rand(n, 3, generator=gen).to(dev)
         for kd in (sx._lib.F32, sx._lib.BF16):
-            k1, f1 = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=kd, want_features=True, impl=sx.ops.FEATURES_TC)
-            k3, f3 = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=kd, want_features=True, impl=sx.ops.FEATURES_TC_STAGED)
+            k1, f1 = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=kd, want_features=True, impl=sx.ops.FEATURES_TC_DIRECT)
+            k3, f3 = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=kd, want_features=True, impl=sx.ops.FEATURES_TC)
             torch.cuda.synchronize()
             assert torch.equal(k1, k3) and torch.equal(f1, f3), (n, kd)
 
@@ -85,9 +61,8 @@ def test_sharded_front_end_two_shards_in_one_process(sx, synthetic, oracle):
     k = 100
     sts = [s._pass1_all(*s._unpack_front(rec, 256, 384)) for s in shards]
     assert all(st["q"][i].is_contiguous() and st["q"][i].data_ptr() % 256 == 0 for st in sts for i in range(2))
-    pm = torch.cat([st["pm"] for st in sts])
-    pz = torch.cat([st["pz"] for st in sts])
-    allc = torch.cat([s._stage2(pm, pz, st, k)[2] for s, st in zip(shards, sts)])
+    pmz = torch.cat([st["pmz"] for st in sts])
+    allc = torch.cat([s._stage2(pmz, st, k)[2] for s, st in zip(shards, sts)])
     for s, st in zip(shards, sts):
         c2w, _ = s._stage3(allc, st["up"], k, st["nb"])
         torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
@@ -137,8 +112,9 @@ def test_multi_query_pipeline_equals_per_query_pipeline(sx, synthetic):
     masks = torch.stack((torch.ones(64, 64, dtype=torch.bool, device=dev), g["mask2"].to(dev),
                          torch.ones(64, 64, dtype=torch.bool, device=dev)))
     cache = idm.build_key_cache(ori, dirs, rgb)
-    ref, _ = sx.ShardedPoseEstimator(idm, ori, dirs, cache).query_batch(imgs, masks)
-    est = sx.ShardedPoseEstimator(idm, ori, dirs, cache, multi_query=True)
+    ref, _ = sx.ShardedPoseEstimator(idm, ori, dirs, cache, multi_query=False).query_batch(imgs, masks)
+    est = sx.ShardedPoseEstimator(idm, ori, dirs, cache)
+    assert est.multi_query  # the default on the tensor-core path
     out, _ = est.query_batch(imgs, masks)
     torch.testing.assert_close(out, ref, rtol=0, atol=0)
     assert est.enable_cuda_graphs(imgs, masks)
@@ -146,35 +122,68 @@ def test_multi_query_pipeline_equals_per_query_pipeline(sx, synthetic):
     torch.testing.assert_close(out_g, ref, rtol=0, atol=0)
 
 
-def test_fused_select_topk_equals_validated_topk(sx):
-    """sixdgs_topk_fused (selection in the last histogram CTA) against sixdgs_topk and torch.topk: values, indices and
-    tie order, incl. heavy ties, negative / denormal / inf values and sizes around the single-CTA threshold"""
+def test_topk_heavy_ties_signed_zero_and_specials(sx):
+    """values always equal torch.topk; ties at the k-th key resolve to the LOWEST indices deterministically, also when
+    there are more ties than the kernel's tie table (4096) holds; -0.0 and +0.0 are one value"""
     dev = "cuda"
     gen = torch.Generator().manual_seed(5)
     cases = []
     for n in (4097, 5000, 100_000, 3_600_000):
         cases.append(torch.rand(n, generator=gen))
         cases.append(torch.randn(n, generator=gen) * 1e-3)
-        cases.append(torch.randint(0, 7, (n,), generator=gen).float())          # heavy ties
+        cases.append(torch.randint(0, 7, (n,), generator=gen).float())          # heavy ties (>> 4096 per value)
         x = torch.randn(n, generator=gen)
         x[::1001] = float("inf")
         x[5::1003] = -float("inf")
         x[7::1009] = 1e-42                                                        # denormals
         cases.append(x)
+        z = torch.zeros(n)                                                        # an (almost) all-masked query
+        z[n - 50:] = 1.0
+        z[1::2] = -0.0
+        cases.append(z)
     for x in cases:
-        x = x.to(dev)
+        xd = x.to(dev)
         for k in (1, 100, 1024):
-            v0, i0 = sx.ops.topk(x, k)
-            v1, i1 = sx.ops.topk(x, k, fused=True)
+            v, i = sx.ops.topk(xd, k)
+            v2, i2 = sx.ops.topk(xd, k)
             torch.cuda.synchronize()
-            assert torch.equal(v0, v1) and torch.equal(i0, i1), (x.shape[0], k)
-            assert torch.equal(v1, torch.topk(x, k).values)
+            assert torch.equal(v, torch.topk(xd, k).values), (x.shape[0], k)
+            assert torch.equal(i, i2) and torch.equal(xd[i], v)
+            # contract: sorted by (value desc, index asc) over the whole input
+            order = torch.sort(x, descending=True, stable=True).indices[:k]  # stable: equal values keep index order
+            assert torch.equal(i.cpu(), order), (x.shape[0], k)
+
+
+def test_no_grad_forward_twice_does_not_reuse_a_stale_key_cache(sx, synthetic):
+    """forward() gathers a fresh random ray subset per call; the implicit key cache must follow the
+    tensors it was built from, not a recycled address"""
+    from conftest import load_golden
+    dev = "cuda"
+    g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
+    ori, dirs, rgb = r["ori"].to(dev), r["dirs"].to(dev), r["rgb"].to(dev)
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone(), score_impl="simt_fp32")
+    idm.load_state_dict(synthetic.synth_id_weights(seed=g["weight_seed"]), strict=False)
+    idm = idm.to(dev).eval().requires_grad_(False)
+    img = g["img"].to(dev)
+    mask = torch.ones(64, 64, dtype=torch.bool, device=dev)
+    with torch.no_grad():
+        for _ in range(4):
+            scores, _, _, _, used = idm(img, mask, ori, dirs, rgb, rays_to_test=2000)
+            o, d, c = ori[used], dirs[used], rgb[used]
+            want, _, _, _ = idm.run_attention(img, mask, o, d, c)
+            torch.testing.assert_close(scores, want, rtol=1e-5, atol=0)
+            ref = idm.score_tokens(idm.backbone_wrapper(img, mask)[0], idm.build_key_cache(o, d, c))[0]
+            torch.testing.assert_close(scores, ref, rtol=1e-5, atol=0)
+    # the same three tensors again hit the cache; an in-place update invalidates it
+    k1 = idm._cache_for(ori, dirs, rgb)
+    assert idm._cache_for(ori, dirs, rgb) is k1
+    ori.add_(0.0)
+    assert idm._cache_for(ori, dirs, rgb) is not k1
 
 
 def test_generate_rays_heavy_tail_vs_reference_fixture(sx, synthetic):
-    """GPU ray generation against the reference-generated heavy-tailed fixture (tests/golden/rays_heavy.npz, added
-    after round 1's GPU budget was spent; the oracle is pinned to it on the CPU).  Promote to test_gpu_parity.py
-    once it has passed on a B200."""
+    """GPU ray generation against the reference-generated heavy-tailed fixture (tests/golden/rays_heavy.npz: 40-6444
+    cells per ellipsoid, the load-imbalance case; the oracle is pinned to it on the CPU)"""
     from conftest import load_golden
     g = load_golden("rays_heavy.npz")
     sc = synthetic.synth_scene(int(g["scene_n"]), seed=int(g["scene_seed"]), heavy_tail=True)

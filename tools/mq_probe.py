@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Sustained comparison of the two ways to score a batch of queries against one bf16 key cache:
-  per-query   8 x (pass 1 + pass 2) of score_tc.cu      -- the default path, 16 sweeps over the keys
-  multi-query 1 x (pass 1 + pass 2) of score_tc_mq.cu   -- EXPERIMENTAL, 2 sweeps
-Each variant runs back to back for `--seconds` so the numbers are taken in the power-capped steady state
-(DESIGN.md §6.1); prints ms per query, the effective key bandwidth and tensor rate, and the SM clock.
+"""Sustained rates of the ray-score kernels on one key cache, each variant run back to back for `--seconds` so the
+numbers are taken in the power-capped steady state:
+  bf16  per-query   B x (pass 1 + pass 2) of score_tc.cu            -- 2B sweeps over 768-B keys, 1 MMA term
+  bf16  multi-query 1 x (pass 1 + pass 2) of score_tc_mq.cu<bf16>   -- 2 sweeps
+  f16x2 multi-query 1 x (pass 1 + pass 2) of score_tc_mq.cu<f16x2>  -- 2 sweeps over 1536-B keys, 3 MMA terms (exact mode)
+Prints ms per query, the MMA rate (terms counted), the HBM rate of the keys actually read, and clocks / power.
 Run it under a shell `timeout` on the GPU box: a tcgen05 kernel with a barrier mistake hangs rather than fails."""
 import argparse
 import importlib
@@ -20,30 +21,33 @@ sx = importlib.import_module("6dgs_b200")
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=12_000_000)
-ap.add_argument("--batch", type=int, default=8)
-ap.add_argument("--seconds", type=float, default=4.0)
+ap.add_argument("--batches", default="8,4,1")
+ap.add_argument("--seconds", type=float, default=3.0)
+ap.add_argument("--variants", default="bf16_pq,bf16_mq,f16x2_mq")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
-B, n = args.batch, args.rays
-K = (torch.randn(n, 384, device=dev) * 0.5).to(torch.bfloat16)
-q = torch.randn(B, 256, 384, device=dev)
+n = args.rays
+kf = torch.randn(n, 384, device=dev) * 0.5
+K16 = kf.to(torch.bfloat16)
+KX = sx.ops.split_keys(kf)
+del kf
 scores1 = torch.empty(n, device=dev)
-scores_b = torch.empty(B, n, device=dev)
 
 
-def per_query():
-    for i in range(B):
+def per_query(K, q, sb):
+    for i in range(q.shape[0]):
         pm, pz = sx.ops.score_pass1(K, q[i], sx.ops.SCORE_TC)
         m, z = sx.ops.score_merge(pm, pz, 256)
         sx.ops.score_pass2(K, q[i], m, z, sx.ops.SCORE_TC, out=scores1)
 
 
-def multi_query():
+def multi_query(K, q, sb):
+    B = q.shape[0]
     pm, pz = sx.ops.score_pass1_batch(K, q)
     parts = pm.shape[0] // B
     mz = [sx.ops.score_merge(pm, pz, 256, rows=parts, first_row=i * parts) for i in range(B)]
-    sx.ops.score_pass2_batch(K, q, torch.stack([x[0] for x in mz]), torch.stack([x[1] for x in mz]), out=scores_b)
+    sx.ops.score_pass2_batch(K, q, torch.stack([x[0] for x in mz]), torch.stack([x[1] for x in mz]), out=sb)
 
 
 def sm_clock():
@@ -55,22 +59,29 @@ def sm_clock():
         return "n/a"
 
 
-for name, fn in (("per-query", per_query), ("multi-query", multi_query), ("per-query", per_query), ("multi-query", multi_query)):
-    fn()
-    torch.cuda.synchronize()
-    t_end = time.perf_counter() + args.seconds
-    times, clk = [], ""
-    while time.perf_counter() < t_end:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        fn()
-        b.record()
-        b.synchronize()
-        times.append(a.elapsed_time(b))
-        if len(times) % 8 == 0:
-            clk = sm_clock()
-    tail = times[len(times) // 2:]  # steady state: second half of the run
-    ms = sum(tail) / len(tail) / B
-    print(f"{name:12s} {ms:7.3f} ms/query  ({len(times)} batches; keys {2 * n * 768 / ms / 1e6:7.1f} GB/s per query-equivalent, "
-          f"{2 * 2 * 256 * 384 * n / ms / 1e9:6.1f} TFLOP/s)  sm MHz, W, power cap: {clk}")
-    time.sleep(3.0)
+VARIANTS = {"bf16_pq": (per_query, K16, 768, 1, False), "bf16_mq": (multi_query, K16, 768, 1, True),
+            "f16x2_mq": (multi_query, KX, 1536, 3, True)}
+for B in [int(b) for b in args.batches.split(",")]:
+    q = torch.randn(B, 256, 384, device=dev)
+    sb = torch.empty(B, n, device=dev)
+    for name in args.variants.split(","):
+        fn, K, row, terms, shared = VARIANTS[name]
+        fn(K, q, sb)
+        torch.cuda.synchronize()
+        t_end = time.perf_counter() + args.seconds
+        times, clk = [], ""
+        while time.perf_counter() < t_end:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(K, q, sb)
+            b.record()
+            b.synchronize()
+            times.append(a.elapsed_time(b))
+            if len(times) % 4 == 0:
+                clk = sm_clock()
+        tail = times[len(times) // 2:]  # steady state: second half of the run
+        ms_batch = sum(tail) / len(tail)
+        sweeps = 2 if shared else 2 * B
+        print(f"B={B} {name:9s} {ms_batch / B:7.3f} ms/query ({len(times)} batches)  MMA {2 * 2 * 256 * 384 * terms * n * B / ms_batch / 1e9:7.1f} "
+              f"TFLOP/s  keys from HBM {sweeps * n * row / ms_batch / 1e6:7.1f} GB/s  sm MHz, W, power cap: {clk}", flush=True)
+        time.sleep(2.0)

@@ -15,7 +15,7 @@ import os
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+KEYS = ["lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -49,7 +49,7 @@ def launches(path, out_md, title):
     return agg, tot
 
 
-def rep_metrics(rep, out_md, out_json, title):
+def rep_metrics(rep, out_md, out_json, title, note=""):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -90,10 +90,8 @@ def rep_metrics(rep, out_md, out_json, title):
                 d = dict(zip(h, r))
                 if d.get("Metric Name") in want:
                     f.write(f"| `{d['Kernel Name'][:32]}` | {d['Section Name']} | {d['Metric Name']} | {d['Metric Value']} | {d['Metric Unit']} |\n")
-            f.write("\nReading: the tensor pipe (\"Compute (SM) Throughput\") is the busiest unit (93 % / 84 %), DRAM runs at 5.5-5.7 TB/s "
-                    "(ncu's percentage is against the 8.19 TB/s nominal peak; 84-87 % of the 6.57 TB/s measured copy peak), the issue "
-                    "slots are 35-38 % busy (the epilogue is not issue-bound), and the SM clock under the profiler is already down to "
-                    "1.32-1.41 GHz from 1.965 GHz: power, not a pipe, sets the speed.\n")
+            if note:
+                f.write("\n" + note + "\n")
     json.dump(traffic, open(out_json, "w"), indent=1)
     return traffic
 
@@ -103,10 +101,13 @@ if __name__ == "__main__":
     ap.add_argument("--round", default="r1")
     ap.add_argument("--launches")
     ap.add_argument("--rep")
+    ap.add_argument("--name", default="score_kernels", help="basename of the summary written under profiles/")
+    ap.add_argument("--note", default="", help="a 'Reading:' paragraph appended to the summary")
     a = ap.parse_args()
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     if a.launches:
         launches(a.launches, os.path.join(ROOT, "profiles", f"launches_{a.round}.md"), f"Launch list of the timed bench steps ({a.round})")
     if a.rep:
-        print(rep_metrics(a.rep, os.path.join(ROOT, "profiles", f"score_kernels_{a.round}.md"),
-                          os.path.join(ROOT, "profiles", f"ncu_profiled_{a.round}.json"), f"Ray-score kernels, ncu --set full ({a.round})"))
+        print(rep_metrics(a.rep, os.path.join(ROOT, "profiles", f"{a.name}_{a.round}.md"),
+                          os.path.join(ROOT, "profiles", f"ncu_profiled_{a.name}_{a.round}.json"),
+                          f"{a.name}, ncu --set full ({a.round})", a.note))
