@@ -35,7 +35,7 @@ _SIGNATURES = {
     "sixdgs_knn_normals_grid": ([c_p, c_i64, c_i64, c_i64, c_i, c_p, ctypes.c_float, c_p, c_p, c_p, c_sz, c_p], c_i),
     "sixdgs_sym_eig3x3": ([c_p, c_i64, ctypes.c_float, c_p, c_p, c_p], c_i),
     "sixdgs_raygen_count": ([c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_i, c_i, c_p, c_p, c_p], c_i),
-    "sixdgs_raygen_fill": ([c_p, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p], c_i),
+    "sixdgs_raygen_fill": ([c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_i64, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p], c_i),
     "sixdgs_exclusive_scan": ([c_p, c_i64, c_p, c_p], c_i),
     "sixdgs_ray_features_workspace": ([c_i64], c_sz),
     "sixdgs_ray_features": ([c_p, c_p, c_p, c_i64] + [c_p] * 10 + [c_p, c_i, c_p, c_i, c_p, c_sz, c_p], c_i),
@@ -53,7 +53,7 @@ _SIGNATURES = {
     "sixdgs_split_keys": ([c_p, c_i64, c_p, c_p, c_p], c_i),
     "sixdgs_ls_partial_rows": ([], c_i),
     "sixdgs_score_pass2_batch_ls": ([c_p, c_i, c_i64, c_p, c_i, c_i, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_sz, c_p], c_i),
-    "sixdgs_ls_solve": ([c_p, c_i, ctypes.c_double, c_p, c_p, c_p, c_p], c_i),
+    "sixdgs_ls_solve": ([c_p, c_i, ctypes.c_double, c_p, c_p, c_p, c_p, c_p, c_p, c_p], c_i),
     "sixdgs_topk_workspace": ([c_i64, c_i], c_sz),
     "sixdgs_topk": ([c_p, c_i64, c_i, c_p, c_p, c_p, c_sz, c_p], c_i),
     "sixdgs_line_intersect": ([c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p], c_i),

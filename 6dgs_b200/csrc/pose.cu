@@ -111,6 +111,71 @@ __global__ void ls_solve_kernel(const double* __restrict__ acc, float* __restric
   if (status) *status = st;
 }
 
+// make_rotation_mat(direction = -watch, up): rows [x; y; direction] (line_intersection.py:5-26); c2w = [inv(R) | c]
+// with the reference's guards (test.py:194-198): det < 1e-7 -> identity rotation (status bit 1), any NaN in the result
+// -> identity pose (status bit 2).  Returns the updated status.
+__device__ inline int frame_to_c2w(const float* c, const float* watch, const float* up, int status, float* out) {
+  const float dx = -watch[0], dy = -watch[1], dz = -watch[2];
+  const float ux = up[0], uy = up[1], uz = up[2];
+  float xx = uy * dz - uz * dy, xy = uz * dx - ux * dz, xz = ux * dy - uy * dx;
+  const float xn = sqrtf(xx * xx + xy * xy + xz * xz);
+  xx /= xn; xy /= xn; xz /= xn;
+  float yx = dy * xz - dz * xy, yy = dz * xx - dx * xz, yz = dx * xy - dy * xx;
+  const float yn = sqrtf(yx * yx + yy * yy + yz * yz);
+  yx /= yn; yy /= yn; yz /= yn;
+  float M[9] = {xx, xy, xz, yx, yy, yz, dx, dy, dz};
+  float det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) +
+              M[2] * (M[3] * M[7] - M[4] * M[6]);
+  float inv[9];
+  if (det < 1.0e-7f) {  // NaN compares false, like the reference: NaN falls through to the c2w check
+    status |= 2;
+    for (int i = 0; i < 9; ++i) inv[i] = (i % 4 == 0) ? 1.f : 0.f;
+  } else {
+    const float id = 1.0f / det;
+    inv[0] = (M[4] * M[8] - M[5] * M[7]) * id; inv[1] = (M[2] * M[7] - M[1] * M[8]) * id; inv[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    inv[3] = (M[5] * M[6] - M[3] * M[8]) * id; inv[4] = (M[0] * M[8] - M[2] * M[6]) * id; inv[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+    inv[6] = (M[3] * M[7] - M[4] * M[6]) * id; inv[7] = (M[1] * M[6] - M[0] * M[7]) * id; inv[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+  }
+  const float o[16] = {inv[0], inv[1], inv[2], c[0], inv[3], inv[4], inv[5], c[1],
+                       inv[6], inv[7], inv[8], c[2], 0.f, 0.f, 0.f, 1.f};
+  bool bad = false;
+  for (int i = 0; i < 16; ++i) bad |= (o[i] != o[i]);
+  if (bad) status |= 4;
+  for (int i = 0; i < 16; ++i) out[i] = bad ? ((i % 5 == 0) ? 1.f : 0.f) : o[i];
+  return status;
+}
+
+// All-ray weighted least squares (least_squared_loss.py:62-64, line_intersection.py:75-154) from the 13 sums the
+// pass-2 epilogue of score_tc_mq.cu accumulates: sys = (R xx,xy,xz,yy,yz,zz | q | sum w d | sum w), every sum scaled
+// by `scale` (1 / n_img: weights = score / n_img).  centre = solve(R, q) through the same fp32 LU + det < 1e-7 guard
+// as the top-k path; watch = normalise(sum w d); c2w (nullable) from (centre, watch, up) like test.py:187-198.
+__global__ void ls_system_solve_kernel(const double* __restrict__ sys, int n, double scale, const float* __restrict__ up,
+                                       float* __restrict__ centre, float* __restrict__ watch, float* __restrict__ c2w,
+                                       float* __restrict__ aux, int32_t* __restrict__ status_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const double* s = sys + (int64_t)b * 13;
+  const double acc[12] = {s[0] * scale, s[1] * scale, s[2] * scale, s[1] * scale, s[3] * scale, s[4] * scale,
+                          s[2] * scale, s[4] * scale, s[5] * scale, s[6] * scale, s[7] * scale, s[8] * scale};
+  float c[3];
+  int status = solve_centre(acc, c);
+  const double n2 = sqrt(s[9] * s[9] + s[10] * s[10] + s[11] * s[11]);
+  const float wv[3] = {(float)(s[9] / n2), (float)(s[10] / n2), (float)(s[11] / n2)};
+  if (centre) { centre[b * 3] = c[0]; centre[b * 3 + 1] = c[1]; centre[b * 3 + 2] = c[2]; }
+  if (watch) { watch[b * 3] = wv[0]; watch[b * 3 + 1] = wv[1]; watch[b * 3 + 2] = wv[2]; }
+  if (c2w) {
+    float out[16];
+    status = frame_to_c2w(c, wv, up + b * 3, status, out);
+    for (int i = 0; i < 16; ++i) c2w[b * 16 + i] = out[i];
+  }
+  if (aux) {
+    float* a = aux + b * 8;
+    a[0] = c[0]; a[1] = c[1]; a[2] = c[2]; a[3] = wv[0]; a[4] = wv[1]; a[5] = wv[2]; a[6] = (float)(s[12] * scale);
+    a[7] = (float)status;
+  }
+  if (status_out) status_out[b] = status;
+}
+
 constexpr int kPoseMaxK = 1024;
 
 __global__ void __launch_bounds__(128)
@@ -229,37 +294,9 @@ pose_tail_kernel(const float* __restrict__ rays_ori, const float* __restrict__ r
       const float fn = sqrtf(fx * fx + fy * fy + fz * fz);
       fx /= fn; fy /= fn; fz /= fn;
       if (aux) { aux[0] = s_c[0]; aux[1] = s_c[1]; aux[2] = s_c[2]; aux[3] = fx; aux[4] = fy; aux[5] = fz; aux[6] = (float)n; }
-      // make_rotation_mat(direction = -watch, up): rows [x; y; direction]        line_intersection.py:5-26
-      const float dx = -fx, dy = -fy, dz = -fz;
-      const float ux = up[0], uy = up[1], uz = up[2];
-      float xx = uy * dz - uz * dy, xy = uz * dx - ux * dz, xz = ux * dy - uy * dx;
-      const float xn = sqrtf(xx * xx + xy * xy + xz * xz);
-      xx /= xn; xy /= xn; xz /= xn;
-      float yx = dy * xz - dz * xy, yy = dz * xx - dx * xz, yz = dx * xy - dy * xx;
-      const float yn = sqrtf(yx * yx + yy * yy + yz * yz);
-      yx /= yn; yy /= yn; yz /= yn;
-      float M[9] = {xx, xy, xz, yx, yy, yz, dx, dy, dz};
-      float det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) +
-                  M[2] * (M[3] * M[7] - M[4] * M[6]);
-      int status = s_status;
-      float inv[9];
-      if (det < 1.0e-7f) {  // NaN compares false, like the reference: NaN falls through to the c2w check
-        status |= 2;
-        for (int i = 0; i < 9; ++i) inv[i] = (i % 4 == 0) ? 1.f : 0.f;
-      } else {
-        const float id = 1.0f / det;
-        inv[0] = (M[4] * M[8] - M[5] * M[7]) * id; inv[1] = (M[2] * M[7] - M[1] * M[8]) * id; inv[2] = (M[1] * M[5] - M[2] * M[4]) * id;
-        inv[3] = (M[5] * M[6] - M[3] * M[8]) * id; inv[4] = (M[0] * M[8] - M[2] * M[6]) * id; inv[5] = (M[2] * M[3] - M[0] * M[5]) * id;
-        inv[6] = (M[3] * M[7] - M[4] * M[6]) * id; inv[7] = (M[1] * M[6] - M[0] * M[7]) * id; inv[8] = (M[0] * M[4] - M[1] * M[3]) * id;
-      }
-      float out[16] = {inv[0], inv[1], inv[2], s_c[0], inv[3], inv[4], inv[5], s_c[1],
-                       inv[6], inv[7], inv[8], s_c[2], 0.f, 0.f, 0.f, 1.f};
-      bool bad = false;
-      for (int i = 0; i < 16; ++i) bad |= (out[i] != out[i]);
-      if (bad) {
-        status |= 4;
-        for (int i = 0; i < 16; ++i) out[i] = (i % 5 == 0) ? 1.f : 0.f;
-      }
+      const float wv[3] = {fx, fy, fz};
+      float out[16];
+      const int status = frame_to_c2w(s_c, wv, up, s_status, out);
       for (int i = 0; i < 16; ++i) c2w[i] = out[i];
       if (aux) aux[7] = (float)status;
     }
@@ -284,6 +321,16 @@ extern "C" int sixdgs_line_intersect(const float* points, const float* dirs, con
   }
   ls_solve_kernel<<<1, 32, 0, s>>>((const double*)workspace, centre, status);
   return check_launch("line_intersect");
+}
+
+extern "C" int sixdgs_ls_solve(const double* ls_sys, int n, double weight_scale, const float* up, float* centre, float* watch,
+                               float* c2w, float* aux, int32_t* status, void* stream) {
+  SIXDGS_REQUIRE(ls_sys && (centre || c2w), "null pointer");
+  SIXDGS_REQUIRE(n >= 1, "bad size");
+  SIXDGS_REQUIRE(!c2w || up, "c2w needs the camera-up vectors");
+  ls_system_solve_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(ls_sys, n, weight_scale, up, centre, watch, c2w, aux,
+                                                                          status);
+  return check_launch("ls_solve");
 }
 
 extern "C" int sixdgs_pose_tail(const float* rays_ori, const float* rays_dir, int64_t ray_stride, const int64_t* idx,

@@ -105,7 +105,7 @@ __device__ __forceinline__ float sh_channel(const float* __restrict__ sh, int ch
 template <bool FILL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 raygen_kernel(const float* __restrict__ xyz, const float* __restrict__ scaling_raw,
-              const float* __restrict__ rotation_raw, const float* __restrict__ features, int sh_degree,
+              const float* __restrict__ rotation_raw, const float* __restrict__ features, int sh_degree, int sh_coeffs,
               const int64_t* __restrict__ sel, int64_t m, const float* __restrict__ normals, int target,
               int resolution, int mode, const int64_t* __restrict__ ray_offset,
               int32_t* __restrict__ rays_per_ell, int32_t* __restrict__ cells_per_ell,
@@ -144,7 +144,10 @@ raygen_kernel(const float* __restrict__ xyz, const float* __restrict__ scaling_r
       nx = normals[e * 3 + 0];
       if (FILL) {
         __syncwarp();
-        for (int i = lane; i < 48; i += 32) shc[i] = features[gid * 48 + i];
+        // features is [N, sh_coeffs, 3] (get_features: 1 dc + rest coefficients, gaussian_model.py:136-140); only the
+        // first (deg+1)^2 coefficients are read by eval_sh, whatever the stored count
+        const int used = (sh_degree + 1) * (sh_degree + 1) * 3;
+        for (int i = lane; i < used; i += 32) shc[i] = features[gid * (int64_t)(sh_coeffs * 3) + i];
         __syncwarp();
       }
     }
@@ -312,13 +315,13 @@ extern "C" int sixdgs_raygen_count(const float* xyz, const float* scaling_raw, c
   SIXDGS_REQUIRE(m >= 0 && target_points > 0, "bad size");
   if (m == 0) return SIXDGS_OK;
   raygen_kernel<false><<<raygen_grid(m), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      xyz, scaling_raw, rotation_raw, nullptr, 0, sel, m, normals, target_points, resolution, mode, nullptr,
+      xyz, scaling_raw, rotation_raw, nullptr, 0, 16, sel, m, normals, target_points, resolution, mode, nullptr,
       rays_per_ell, cells_per_ell, nullptr, nullptr, nullptr, nullptr);
   return check_launch("raygen_count");
 }
 
 extern "C" int sixdgs_raygen_fill(const float* xyz, const float* scaling_raw, const float* rotation_raw,
-                                  const float* features, int sh_degree, const int64_t* sel, int64_t m,
+                                  const float* features, int sh_degree, int sh_coeffs, const int64_t* sel, int64_t m,
                                   const float* normals, int target_points, int resolution, int mode,
                                   const int64_t* ray_offset, float* ori, float* dir, float* rgb, int64_t* ell_id,
                                   void* stream) {
@@ -326,11 +329,12 @@ extern "C" int sixdgs_raygen_fill(const float* xyz, const float* scaling_raw, co
   SIXDGS_REQUIRE(mode == 1 || (xyz && rotation_raw && normals && features && dir && rgb),
                  "mode 0 needs xyz, rotation, normals, features, dir and rgb");
   SIXDGS_REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sh_degree must be 0..3");
+  SIXDGS_REQUIRE(mode == 1 || sh_coeffs >= (sh_degree + 1) * (sh_degree + 1), "features hold fewer than (sh_degree+1)^2 coefficients");
   SIXDGS_REQUIRE(resolution >= 2 && resolution <= kTableMax, "resolution must be in [2, 1024]");
   SIXDGS_REQUIRE(m >= 0 && target_points > 0, "bad size");
   if (m == 0) return SIXDGS_OK;
   raygen_kernel<true><<<raygen_grid(m), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      xyz, scaling_raw, rotation_raw, features, sh_degree, sel, m, normals, target_points, resolution, mode,
+      xyz, scaling_raw, rotation_raw, features, sh_degree, sh_coeffs, sel, m, normals, target_points, resolution, mode,
       ray_offset, nullptr, nullptr, ori, dir, rgb, ell_id);
   return check_launch("raygen_fill");
 }

@@ -472,36 +472,6 @@ __global__ void mq_ls_reduce_kernel(const double* __restrict__ part, int n_cta, 
   out[b * kMqLs + j] = a;
 }
 
-// sys [13] = (R6, q3, wd3, w) scaled by `scale` (1 / n_img: weights = score / n_img, least_squared_loss.py:62-64)
-// -> centre = solve(R, q) (NaN x3 and status bit 0 when det(R) < 1e-7, line_intersection.py:139-142), watch = wd / |wd|
-__global__ void mq_ls_solve_kernel(const double* __restrict__ sys, int n, double scale, float* __restrict__ centre,
-                                   float* __restrict__ watch, int* __restrict__ status) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n) return;
-  const double* s = sys + (int64_t)b * kMqLs;
-  const double xx = s[0] * scale, xy = s[1] * scale, xz = s[2] * scale, yy = s[3] * scale, yz = s[4] * scale,
-               zz = s[5] * scale, qx = s[6] * scale, qy = s[7] * scale, qz = s[8] * scale;
-  const double c00 = yy * zz - yz * yz, c01 = xz * yz - xy * zz, c02 = xy * yz - xz * yy;
-  const double det = xx * c00 + xy * c01 + xz * c02;
-  int st = 0;
-  // the reference evaluates det(R) in fp32; compare the fp32-rounded value with its literal threshold
-  if (!((float)det >= 1.0e-7f)) {
-    centre[b * 3 + 0] = centre[b * 3 + 1] = centre[b * 3 + 2] = __int_as_float(0x7fc00000);
-    st = 1;
-  } else {
-    const double c11 = xx * zz - xz * xz, c12 = xy * xz - xx * yz, c22 = xx * yy - xy * xy;
-    centre[b * 3 + 0] = (float)((c00 * qx + c01 * qy + c02 * qz) / det);
-    centre[b * 3 + 1] = (float)((c01 * qx + c11 * qy + c12 * qz) / det);
-    centre[b * 3 + 2] = (float)((c02 * qx + c12 * qy + c22 * qz) / det);
-  }
-  if (watch) {
-    const double n2 = sqrt(s[9] * s[9] + s[10] * s[10] + s[11] * s[11]);
-    const double inv = n2 > 1e-300 ? 1.0 / n2 : 0.0;
-    watch[b * 3 + 0] = (float)(s[9] * inv); watch[b * 3 + 1] = (float)(s[10] * inv); watch[b * 3 + 2] = (float)(s[11] * inv);
-  }
-  if (status) status[b] = st;
-}
-
 template <bool SPLIT>
 int mq_make_map(CUtensorMap* map, const void* base, uint64_t rows) {
   constexpr int row = MqCfg<SPLIT>::kRow;
@@ -610,14 +580,6 @@ extern "C" int sixdgs_score_pass2_batch_ls(const void* k_cache, int k_dtype, int
   if (rc) return rc;
   mq_ls_reduce_kernel<<<n_queries, 32, 0, (cudaStream_t)stream>>>(ls_part, kMqPairs * 2, ls_sys);
   return check_launch("ls_reduce");
-}
-
-extern "C" int sixdgs_ls_solve(const double* ls_sys, int n, double weight_scale, float* centre, float* watch,
-                               int32_t* status, void* stream) {
-  SIXDGS_REQUIRE(ls_sys && centre, "null pointer");
-  SIXDGS_REQUIRE(n >= 1, "bad size");
-  mq_ls_solve_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(ls_sys, n, weight_scale, centre, watch, status);
-  return check_launch("ls_solve");
 }
 
 extern "C" int sixdgs_split_keys(const float* k_f32, int64_t n, void* k_out, float* absmax, void* stream) {

@@ -114,7 +114,13 @@ def raygen(xyz, scaling_raw, rotation_raw, features, sh_degree: int, sel: torch.
         dirs = torch.empty(n_rays, 3, dtype=torch.float32, device=dev)
         rgb = torch.empty(n_rays, 3, dtype=torch.float32, device=dev)
     if n_rays:
-        call("sixdgs_raygen_fill", dptr(xyz), dptr(scaling_raw), dptr(rotation_raw), dptr(features), sh_degree,
+        sh_coeffs = 16
+        if features is not None:
+            if features.dim() != 3 or features.shape[2] != 3 or features.shape[1] < (sh_degree + 1) ** 2:
+                raise _lib.SixdgsError(f"features must be [N, >= (sh_degree+1)^2, 3] (get_features layout); got "
+                                       f"{tuple(features.shape)} for sh_degree {sh_degree}")
+            sh_coeffs = int(features.shape[1])
+        call("sixdgs_raygen_fill", dptr(xyz), dptr(scaling_raw), dptr(rotation_raw), dptr(features), sh_degree, sh_coeffs,
              dptr(sel, torch.int64), m, dptr(normals), target_points, resolution, mode, dptr(offs, torch.int64),
              dptr(ori), dptr(dirs), dptr(rgb), dptr(ell, torch.int64), s)
     return ori, dirs, rgb, ell, cells_per
@@ -332,16 +338,23 @@ def score_pass2_batch(k_cache: torch.Tensor, q: torch.Tensor, m: torch.Tensor, z
     return scores if ls_rays is None else (scores, ls_sys)
 
 
-def ls_solve(ls_sys: torch.Tensor, weight_scale: float = 1.0):
+def ls_solve(ls_sys: torch.Tensor, weight_scale: float = 1.0, up: Optional[torch.Tensor] = None):
     """ls_sys [B,13] float64 (summed over shards) -> (centre [B,3], watch [B,3], status [B] int32); the sums are scaled
-    by weight_scale first (1 / n_img: weights = score / n_img, least_squared_loss.py:62-64)."""
+    by weight_scale first (1 / n_img: weights = score / n_img, least_squared_loss.py:62-64).
+    With up [B,3] (unit camera-up vectors): -> (c2w [B,4,4], aux [B,8]) like the tail of the top-k path."""
     nb = ls_sys.shape[0]
     dev = ls_sys.device
+    if up is not None:
+        c2w = torch.empty(nb, 4, 4, dtype=torch.float32, device=dev)
+        aux = torch.empty(nb, 8, dtype=torch.float32, device=dev)
+        call("sixdgs_ls_solve", dptr(ls_sys, torch.float64), nb, ctypes.c_double(weight_scale), dptr(f32c(up)), None, None,
+             dptr(c2w), dptr(aux), None, stream_ptr())
+        return c2w, aux
     centre = torch.empty(nb, 3, dtype=torch.float32, device=dev)
     watch = torch.empty(nb, 3, dtype=torch.float32, device=dev)
     status = torch.zeros(nb, dtype=torch.int32, device=dev)
-    call("sixdgs_ls_solve", dptr(ls_sys, torch.float64), nb, ctypes.c_double(weight_scale), dptr(centre), dptr(watch),
-         dptr(status, torch.int32), stream_ptr())
+    call("sixdgs_ls_solve", dptr(ls_sys, torch.float64), nb, ctypes.c_double(weight_scale), None, dptr(centre), dptr(watch),
+         None, None, dptr(status, torch.int32), stream_ptr())
     return centre, watch, status
 
 

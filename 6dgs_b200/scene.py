@@ -20,12 +20,19 @@ class GaussianScene:
         self._xyz = f(xyz)
         self._scaling = f(scaling)
         self._rotation = f(rotation)
-        self._features = torch.cat((f(features_dc), f(features_rest)), dim=1).contiguous()  # [N,16,3]
-        self.active_sh_degree = sh_degree
-        self.max_sh_degree = sh_degree
+        # [N, (max_deg+1)^2, 3]: 16 coefficients for the usual degree-3 storage, fewer for low-degree models.  A model
+        # may be evaluated below its stored degree (3DGS raises active_sh_degree during training, gaussian_model.py:121-123)
+        self._features = torch.cat((f(features_dc), f(features_rest)), dim=1).contiguous()
         n = self._xyz.shape[0]
         assert self._scaling.shape == (n, 3) and self._rotation.shape == (n, 4)
-        assert self._features.shape == (n, (sh_degree + 1) ** 2, 3)
+        nc = self._features.shape[1]
+        self.max_sh_degree = int(round(nc ** 0.5)) - 1
+        if self._features.shape != (n, nc, 3) or (self.max_sh_degree + 1) ** 2 != nc:
+            raise ValueError(f"SH features must be [N, (deg+1)^2, 3], got {tuple(self._features.shape)}")
+        if not 0 <= sh_degree <= min(self.max_sh_degree, 3):
+            raise ValueError(f"active sh_degree {sh_degree} outside 0..min(stored degree {self.max_sh_degree}, 3) "
+                             "(eval_sh on the pose path goes up to degree 3, sampling.py:116-124)")
+        self.active_sh_degree = sh_degree
 
     @classmethod
     def from_dict(cls, d, device=None):

@@ -61,6 +61,13 @@ class CudaBackend:
     def pass2_batch(self, keys, q, m, z, out):
         return ops.score_pass2_batch(keys, q, m, z, out=out)
 
+    def pass2_batch_ls(self, keys, q, m, z, out, ori, dirs):
+        """pass 2 + the all-ray weighted least-squares system in its epilogue -> (scores [B,n], ls_sys [B,13] float64)"""
+        return ops.score_pass2_batch(keys, q, m, z, out=out, ls_rays=(ori, dirs))
+
+    def ls_solve(self, ls_sys, weight_scale, up):
+        return ops.ls_solve(ls_sys, weight_scale, up)
+
     def topk(self, scores, k):
         return ops.topk(scores, k)
 
@@ -90,12 +97,22 @@ class ShardedPoseEstimator:
 
     ``multi_query`` (tensor-core path only; default: on for it): score the whole batch in one sweep over the key cache
     per pass (csrc/score_tc_mq.cu) instead of one sweep per query -- bit-identical scores, the keys cross HBM once per
-    pass per batch."""
+    pass per batch.
+
+    ``solve``: "topk" (default) is the reference's evaluation path (test.py:85-198): top-100 rays, dedup, unweighted LS,
+    watch direction from the re-weighted winners; across shards the local winners are all-gathered.  "weighted_ls" is the
+    all-ray weighted least squares of least_squared_loss.py:47-64 (weights = score / n_img over EVERY ray): the 3x3
+    system, sum w d and sum w are accumulated in the pass-2 epilogue, the shards' 13-double systems are summed by ONE
+    all-reduce, and the pose comes from (centre, normalised sum w d, camera up) -- no top-k at all.  Needs the batched
+    tensor-core kernel (multi_query)."""
 
     def __init__(self, idm, rays_ori: torch.Tensor, rays_dir: torch.Tensor, cache, rank: int = 0, world: int = 1,
-                 backend=None, group=None, front_end: str = "replicated", multi_query: Optional[bool] = None):
+                 backend=None, group=None, front_end: str = "replicated", multi_query: Optional[bool] = None,
+                 solve: str = "topk"):
         if front_end not in ("replicated", "sharded"):
             raise ValueError(f"front_end must be 'replicated' or 'sharded', got {front_end!r}")
+        if solve not in ("topk", "weighted_ls"):
+            raise ValueError(f"solve must be 'topk' or 'weighted_ls', got {solve!r}")
         self.backend = backend or CudaBackend(idm)
         self.ori, self.dirs, self.cache = rays_ori, rays_dir, cache
         self.rank, self.world, self.group = rank, world, group
@@ -105,6 +122,9 @@ class ShardedPoseEstimator:
         self.multi_query = bool(multi_query)
         if self.multi_query and getattr(self.backend, "impl", ops.SCORE_TC) != ops.SCORE_TC:
             raise ValueError("multi_query needs the tensor-core score path (score_impl='tc_bf16')")
+        self.solve = solve
+        if solve == "weighted_ls" and not self.multi_query:
+            raise ValueError("solve='weighted_ls' needs the batched tensor-core score kernel (multi_query)")
         self._scores_b = None  # [B, n_rays] score rows of a batch (multi_query)
         self.parts = getattr(self.backend, "parts", 1)
         if cache.scores is None:
@@ -246,6 +266,31 @@ class ShardedPoseEstimator:
                 b.candidates(v, ix, self.ori, self.dirs, k, cand[i])
         return vals, idxs, cand
 
+    def _all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def _stage2_weighted(self, pmz, st):
+        """merged statistics -> scores + this shard's weighted least-squares system per query, ls_sys [B,13] float64"""
+        b = self.backend
+        nb, rows = st["nb"], st["rows"]
+        groups = pmz.shape[0] // (2 * nb * rows)
+        pm, pz = pmz, pmz[nb * rows:]
+        mz = [b.merge(pm, pz, st["n_img"], st["valid"][i] if st["valid"] is not None else None, rows=rows, groups=groups,
+                      group_stride=2 * nb * rows, first_row=i * rows) for i in range(nb)]
+        if self._scores_b is None or self._scores_b.shape[0] < nb:
+            self._scores_b = torch.empty((nb, self.cache.n_rays), dtype=torch.float32, device=self.ori.device)
+        _, ls_sys = b.pass2_batch_ls(self.cache.keys, st["q"], torch.stack([x[0] for x in mz]),
+                                     torch.stack([x[1] for x in mz]), self._scores_b[:nb], self.ori, self.dirs)
+        return ls_sys
+
+    def _stage3_weighted(self, ls_sys, st):
+        """summed systems -> poses.  weights = score / n_img with n_img the number of valid tokens of the query; the
+        scale only matters for the det(R) < 1e-7 guard, the solution is scale-free"""
+        return self.backend.ls_solve(ls_sys, 1.0 / st["n_img"], st["up"][:st["nb"]].contiguous())
+
     def _stage3(self, allc, up, k, nb):
         """allc [world * B, k, 7] (rank-major) -> per-query global top-k -> pose"""
         b = self.backend
@@ -268,6 +313,11 @@ class ShardedPoseEstimator:
         pmz = st["pmz"]
         if self.world > 1:
             pmz = self._all_gather(pmz)
+        if self.solve == "weighted_ls":
+            ls_sys = self._stage2_weighted(pmz, st)
+            if self.world > 1:
+                ls_sys = self._all_reduce_sum(ls_sys)
+            return self._stage3_weighted(ls_sys, st)
         vals, idxs, cand = self._stage2(pmz, st, k)
         if self.world == 1:
             outs = [self.backend.pose_tail(self.ori, self.dirs, idxs[i], vals[i], st["up"][i]) for i in range(st["nb"])]
@@ -314,11 +364,18 @@ class ShardedPoseEstimator:
                     with torch.cuda.graph(g1):
                         g["st"] = self._stage1(g["img"], g["mask"])
                 g["pmz_all"] = self._all_gather(g["st"]["pmz"])
-                with torch.cuda.graph(g2):
-                    _, _, g["cand"] = self._stage2(g["pmz_all"], g["st"], k)
-                g["allc"] = self._all_gather(g["cand"])
-                with torch.cuda.graph(g3):
-                    g["out"] = self._stage3(g["allc"], g["st"]["up"], k, g["st"]["nb"])
+                if self.solve == "weighted_ls":
+                    with torch.cuda.graph(g2):
+                        g["ls_sys"] = self._stage2_weighted(g["pmz_all"], g["st"])
+                    self._all_reduce_sum(g["ls_sys"])
+                    with torch.cuda.graph(g3):
+                        g["out"] = self._stage3_weighted(g["ls_sys"], g["st"])
+                else:
+                    with torch.cuda.graph(g2):
+                        _, _, g["cand"] = self._stage2(g["pmz_all"], g["st"], k)
+                    g["allc"] = self._all_gather(g["cand"])
+                    with torch.cuda.graph(g3):
+                        g["out"] = self._stage3(g["allc"], g["st"]["up"], k, g["st"]["nb"])
                 g["graphs"] = [g1, g2, g3]
             torch.cuda.synchronize()
             self._g = g
@@ -347,7 +404,10 @@ class ShardedPoseEstimator:
             g["graphs"][0].replay()
             self._all_gather(g["st"]["pmz"], g["pmz_all"])
             g["graphs"][1].replay()
-            self._all_gather(g["cand"], g["allc"])
+            if self.solve == "weighted_ls":
+                self._all_reduce_sum(g["ls_sys"])  # in place on the graph's static buffer (rewritten by every replay)
+            else:
+                self._all_gather(g["cand"], g["allc"])
             g["graphs"][2].replay()
         return g["out"]
 

@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gaussians", type=int, default=1_000_000)
+    ap.add_argument("--gaussians", type=int, default=None)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--score-impl", default="tc_f16x2", choices=["tc_f16x2", "tc_bf16", "simt_bf16", "simt_fp32"],
@@ -71,11 +71,24 @@ def parse():
     ap.add_argument("--per-query-sweeps", action="store_true",
                     help="score each query with its own two sweeps over the key cache instead of one sweep per pass "
                          "for the whole batch (tensor-core modes default to the batched kernel)")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the bf16 throughput-mode figure")
-    ap.add_argument("--batch", type=int, default=8,
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary figures (bf16 throughput mode, weighted-LS solve)")
+    ap.add_argument("--solve", choices=("topk", "weighted_ls"), default="topk",
+                    help="topk = the reference's evaluation path (top-100 rays -> LS, test.py:85-198); weighted_ls = all-ray "
+                         "weighted least squares fused into the pass-2 epilogue + one all-reduce (least_squared_loss.py:47-64)")
+    ap.add_argument("--config", choices=("c3", "c5"), default="c3",
+                    help="c3 = BASELINE configs[2]/[3] (1M Gaussians, 8 queries per step); c5 = configs[4] (5M Gaussians, "
+                         "32 queries per step, 8 GPUs); explicit --gaussians / --batch override")
+    ap.add_argument("--no-latency", action="store_true", help="skip the one-query-per-step figure (profiling runs)")
+    ap.add_argument("--no-breakdown", action="store_true", help="skip the eager per-stage CUDA-event breakdown")
+    ap.add_argument("--batch", type=int, default=None,
                     help="queries per step: the image front end (resize, backbone, q projection, up head) runs once per "
                          "batch, the key cache is streamed per query; 1 = one query per step")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.gaussians is None:
+        args.gaussians = 5_000_000 if args.config == "c5" else 1_000_000
+    if args.batch is None:
+        args.batch = 32 if args.config == "c5" else 8
+    return args
 
 
 def load_peaks():
@@ -256,6 +269,53 @@ def time_score_kernels(sx, idm, cache, dev, warm, iters, nq, batched):
     return p1, p2
 
 
+def stage_breakdown(est, imgs, masks, local, world, reps=3):
+    """ms per batch of each pipeline stage, eager launches bracketed by CUDA events (mean of `reps` after one warm-up).
+    front = image front end (+ its all-gather when sharded); pass1 = statistics sweep; gather = the statistics
+    all-gather; stage2 = merge + score sweep + per-query top-k / LS system; exchange = candidate all-gather or
+    system all-reduce; tail = global top-k + pose tails.  The sum is larger than a graph-replayed step (launch gaps)."""
+    names = ("front", "pass1", "gather_stats", "stage2", "exchange", "tail")
+    acc = {k: 0.0 for k in names}
+    for it in range(reps + 1):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+        ev[0].record()
+        if est._shards_front(imgs.shape[0], local):
+            q, up, valid = est._front(*est._local_chunk(imgs, masks, local))
+            rec = est._all_gather(est._pack_front(q, up, valid))
+            front = est._unpack_front(rec, q.shape[1], q.shape[2])
+        else:
+            front = est._front(imgs, masks)
+        ev[1].record()
+        st = est._pass1_all(*front)
+        ev[2].record()
+        pmz = est._all_gather(st["pmz"]) if world > 1 else st["pmz"]
+        ev[3].record()
+        if est.solve == "weighted_ls":
+            ls_sys = est._stage2_weighted(pmz, st)
+            ev[4].record()
+            if world > 1:
+                ls_sys = est._all_reduce_sum(ls_sys)
+            ev[5].record()
+            est._stage3_weighted(ls_sys, st)
+        else:
+            vals, idxs, cand = est._stage2(pmz, st, 100)
+            ev[4].record()
+            allc = est._all_gather(cand) if world > 1 else None
+            ev[5].record()
+            if world > 1:
+                est._stage3(allc, st["up"], 100, st["nb"])
+            else:
+                [est.backend.pose_tail(est.ori, est.dirs, idxs[i], vals[i], st["up"][i]) for i in range(st["nb"])]
+        ev[6].record()
+        torch.cuda.synchronize()
+        if it:
+            for i, k in enumerate(names):
+                acc[k] += ev[i].elapsed_time(ev[i + 1]) / reps
+    acc["total"] = sum(acc[k] for k in names)
+    acc["queries_per_batch"] = int(st["nb"])
+    return acc
+
+
 def expected_rays(n_gaussians):
     return int(n_gaussians * 29.05)
 
@@ -289,11 +349,11 @@ def run_reference_arm(args):
 def workload_config(args, n_rays, n_rays_local):
     batched = args.score_impl.startswith("tc_") and not args.per_query_sweeps
     return {"workload": f"{args.gaussians} synthetic Gaussians (all valid ellipsoids, uncapped), {args.height}x{args.width} "
-                        f"image, {args.score_impl} key cache, fp32 LS solve (BASELINE.json configs[2])",
+                        f"image, {args.score_impl} key cache, fp32 LS solve (BASELINE.json configs[{4 if args.config == 'c5' else (2 if args.gpus == 1 else 3)}])",
             "gaussians": args.gaussians, "n_rays": n_rays, "n_rays_per_rank": n_rays_local, "image": [args.height, args.width],
             "n_img_tokens": 256, "queries_per_step": args.batch, "score_impl": args.score_impl, "backbone": args.backbone, "backbone_matmul": args.backbone_matmul,
             "front_end": args.front_end if args.gpus > 1 else "single",
-            "score_sweeps": "per batch (multi-query kernel)" if batched else "per query",
+            "score_sweeps": "per batch (multi-query kernel)" if batched else "per query", "solve": args.solve,
             "parallelism": f"ray-shard x{args.gpus}", "l2": "inputs larger than L2 (key cache >> 126 MB), no flush needed"}
 
 
@@ -306,10 +366,11 @@ def build_roofline(args, peaks, n_local, nq, burst, sustained, batched, sm_mhz, 
     kernel serves nq queries from one sweep; in f16x2 mode the lo halves are re-read per query from L2, not HBM) plus
     the outputs; MMA FLOPs per launch: 2 * 256 tokens * 384 * terms per ray per query."""
     row_bytes, terms, _ = KEY_FORMATS[args.score_impl]
-    n_launch_q = nq if batched else 1
+    n_launch_q = nq if batched else 1          # queries covered by one timed pass
+    sweeps = -(-n_launch_q // 8)               # the batched kernel takes up to 8 queries per launch (one key sweep each)
     flops = 2.0 * 256 * 384 * terms * n_local * n_launch_q
-    bytes_p = {"pass1": n_local * row_bytes + n_launch_q * 74 * 2 * 256 * 4,
-               "pass2": n_local * row_bytes + n_launch_q * n_local * 4}
+    bytes_p = {"pass1": sweeps * n_local * row_bytes + n_launch_q * 74 * 2 * 256 * 4,
+               "pass2": sweeps * n_local * row_bytes + n_launch_q * n_local * 4}
     name = "score_tc_mq_kernel" if batched else ("score_tc_kernel" if args.score_impl.startswith("tc_") else "score_simt_kernel")
 
     def view(ms, which, tensor_peak):
@@ -323,6 +384,7 @@ def build_roofline(args, peaks, n_local, nq, burst, sustained, batched, sm_mhz, 
                    "figure); sustained = right after it in the timed region's thermal / power state (tensor roof = cuBLAS "
                    "sustained figure); `achieved` / `frac` are the sustained figures of the slower pass",
            "algorithmic_bytes_per_launch": bytes_p, "mma_flops_per_launch": flops, "queries_per_launch": n_launch_q,
+           "kernel_launches_per_pass": sweeps,
            "key_row_bytes": row_bytes, "mma_terms_per_logit": terms,
            "tensor_peak_at_sampled_clock_tflops": (peaks["bf16_tflops"] * sm_mhz / sm_max_mhz) if sm_mhz and sm_max_mhz else None}
     dom = max(det["sustained"], key=lambda k: det["sustained"][k]["ms"])
@@ -400,7 +462,8 @@ def main():
         t = torch.tensor([n_local], device=dev, dtype=torch.long)
         dist.all_reduce(t)
         n_total = int(t.item())
-    est = sharding.ShardedPoseEstimator(idm, ori, dirs, cache, rank, world, front_end=args.front_end, multi_query=batched)
+    est = sharding.ShardedPoseEstimator(idm, ori, dirs, cache, rank, world, front_end=args.front_end, multi_query=batched,
+                                        solve=args.solve)
 
     B = args.batch
     img_u8 = torch.stack([(sx.synthetic.synth_image(args.height, args.width, seed=7 + i) * 255).to(torch.uint8) for i in range(B)])
@@ -418,7 +481,7 @@ def main():
 
     # one-query-per-step latency figure (eager + its own graphs), measured before the batched graphs are captured
     lat_b1 = None
-    if B > 1:
+    if B > 1 and not args.no_latency:
         for _ in range(3):
             est.query_batch(img_dev[:1], mask_dev[:1])
         if not args.no_graph:
@@ -484,6 +547,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = B * args.steps / (ms / 1e3)
+
+    # ---------------- eager per-stage breakdown (CUDA events, outside the timed region; what does not shrink with N) -----
+    breakdown = None
+    if not args.no_breakdown:
+        breakdown = stage_breakdown(est, img_q, mask_q, own_only, world)
 
     # ---------------- e2e: host image -> pose on host, through the public API ----------------
     pose_host = torch.empty(B, 4, 4).pin_memory()
@@ -569,7 +637,7 @@ def main():
                 "data": "synthetic", "config": workload_config(args, n_total, n_local), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": (lpq * B + lpb) * args.steps, "cuda_graph": bool(graph),
                 "queries_per_step": B, "latency_b1": {"ms_per_query": lat_b1, "queries_per_s": (1e3 / lat_b1) if lat_b1 else None},
-                "roofline": roofline, "cpu_baseline": cpu, "throughput_mode": secondary,
+                "roofline": roofline, "cpu_baseline": cpu, "throughput_mode": secondary, "breakdown_ms_per_batch": breakdown,
                 "parity": "tests/test_gpu_exact_tc.py (scores <= 1e-3 rel, pose <= 1e-4 vs the reference fixtures incl. a peaked "
                           "softmax, and every score of this 1M-Gaussian scene vs fp64)" if args.score_impl == "tc_f16x2" else
                           "throughput / alternative mode; see tests/test_gpu_parity.py for its tolerance",

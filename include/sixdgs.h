@@ -88,7 +88,8 @@ int sixdgs_raygen_count(const float* xyz, const float* scaling_raw, const float*
                         int resolution, int mode, int32_t* rays_per_ell, int32_t* cells_per_ell,
                         void* stream);
 int sixdgs_raygen_fill(const float* xyz, const float* scaling_raw, const float* rotation_raw,
-                       const float* features /* [N,16,3] = get_features */, int sh_degree,
+                       const float* features /* [N,sh_coeffs,3] = get_features */, int sh_degree,
+                       int sh_coeffs /* stored coefficients per Gaussian, >= (sh_degree+1)^2; 16 for degree-3 storage */,
                        const int64_t* sel, int64_t m, const float* normals, int target_points,
                        int resolution, int mode, const int64_t* ray_offset, float* ori, float* dir,
                        float* rgb, int64_t* ell_id, void* stream);
@@ -170,15 +171,17 @@ int sixdgs_score_pass2_batch(const void* k_cache, int k_dtype, int64_t n_rays, c
  *   R = sum w (I - d d^T) as (xx,xy,xz,yy,yz,zz), q = sum w (I - d d^T) o (3), sum w d (3), sum w
  * ls_part [n_queries, sixdgs_ls_partial_rows(), 13] = per-CTA partial sums (scratch), ls_sys [n_queries, 13] = their
  * sum in a fixed order.  Across ray shards the systems simply add: one 13-double all-reduce per query.
- * sixdgs_ls_solve: centre = solve(R, q) after scaling every sum by weight_scale (1 / n_img in the reference);
- * NaN x3 and status |= 1 when det(R) < 1e-7; watch (nullable) = normalised sum w d. */
+ * sixdgs_ls_solve (n systems): centre[n,3] = solve(R, q) after scaling every sum by weight_scale (1 / n_img in the
+ * reference); NaN x3 and status |= 1 when det(R) < 1e-7; watch[n,3] (nullable) = normalised sum w d; c2w[n,16]
+ * (nullable, needs up[n,3]) = pose from (centre, watch, up) exactly like the tail of the top-k path (test.py:187-198);
+ * aux[n,8] (nullable) = centre3, watch3, sum of weights, status. */
 int sixdgs_ls_partial_rows(void);
 int sixdgs_score_pass2_batch_ls(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries,
                                 int n_img, const float* m, const float* z, float* scores, int64_t score_stride,
                                 const float* rays_ori, const float* rays_dir, double* ls_part, double* ls_sys,
                                 void* workspace, size_t workspace_bytes, void* stream);
-int sixdgs_ls_solve(const double* ls_sys, int n, double weight_scale, float* centre, float* watch, int32_t* status,
-                    void* stream);
+int sixdgs_ls_solve(const double* ls_sys, int n, double weight_scale, const float* up, float* centre, float* watch,
+                    float* c2w, float* aux, int32_t* status, void* stream);
 
 /* ---- a12: top-k -------- identification_module.py:131 (torch.topk, sorted descending) -----------
  * workspace >= sixdgs_topk_workspace(n, k).  idx int64, ties broken by lower index first. */

@@ -198,3 +198,73 @@ def test_generate_rays_heavy_tail_vs_reference_fixture(sx, synthetic):
         for mine, ref in ((ori, g["ori_s"]), (dirs, g["dirs_s"]), (rgb, g["rgb_s"])):
             frac = ((mine[::8].cpu() - ref).abs().max(dim=1).values <= 1e-5).float().mean().item()
             assert frac >= 0.985, frac
+
+
+def test_weighted_least_squares_solve_mode_single_gpu_and_two_shards(sx, synthetic, oracle):
+    """ShardedPoseEstimator(solve="weighted_ls"): all-ray weighted LS fused into the pass-2 epilogue, against the oracle's
+    compute_line_intersection_impl2(ori, -dir, score / n_img) (least_squared_loss.py:62-64) on the kernel's own scores;
+    two emulated shards (systems summed, as the all-reduce does) give the unsharded pose; CUDA graphs replay it."""
+    from conftest import load_golden
+    dev = "cuda"
+    g, r = load_golden("id_module_peaked.npz"), load_golden("rays_small.npz")
+    ori, dirs, rgb = r["ori"].to(dev), r["dirs"].to(dev), r["rgb"].to(dev)
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone(), score_impl="tc_f16x2")
+    idm.load_state_dict(synthetic.synth_id_weights(seed=3, q_gain=float(g["q_gain"])), strict=False)
+    idm = idm.to(dev).eval().requires_grad_(False)
+    img = g["img"].to(dev)
+    imgs = torch.stack((img, img.flip(1), img * 0.7))
+    masks = torch.ones(3, 64, 64, dtype=torch.bool, device=dev)
+    cache = idm.build_key_cache(ori, dirs, rgb)
+    est = sx.ShardedPoseEstimator(idm, ori, dirs, cache, solve="weighted_ls")
+    c2w, aux = est.query_batch(imgs, masks)
+    for i in range(3):
+        _, _, scores, up, _ = idm.test_image(imgs[i], masks[i], ori, dirs, rgb)
+        w = scores.cpu() / 256
+        centre = oracle.line_intersection(r["ori"].double(), -r["dirs"].double(), w.double()).float()
+        watch = torch.nn.functional.normalize((w[:, None].double() * r["dirs"].double()).sum(0), dim=0).float()
+        torch.testing.assert_close(c2w[i, :3, 3].cpu(), centre, rtol=1e-4, atol=1e-4)
+        rot = torch.linalg.inv(oracle.make_rotation_mat(-watch, up.cpu()))
+        torch.testing.assert_close(c2w[i, :3, :3].cpu(), rot, rtol=1e-4, atol=1e-4)
+        assert aux[i, 7].item() == 0
+    # two shards: per-shard systems add up to the whole (what the single all-reduce computes)
+    n = ori.shape[0]
+    cut = n // 2 + 11
+    st = est._stage1(imgs, masks)
+    sys_full = est._stage2_weighted(st["pmz"], st)
+    shards = []
+    for rank, (lo, hi) in enumerate(((0, cut), (cut, n))):
+        o, d, c = ori[lo:hi].contiguous(), dirs[lo:hi].contiguous(), rgb[lo:hi].contiguous()
+        shards.append(sx.ShardedPoseEstimator(idm, o, d, idm.build_key_cache(o, d, c), rank, 2, solve="weighted_ls"))
+    sts = [s._stage1(imgs, masks) for s in shards]
+    pmz = torch.cat([s_["pmz"] for s_ in sts])
+    sys_sum = sum(s._stage2_weighted(pmz, s_) for s, s_ in zip(shards, sts))
+    torch.testing.assert_close(sys_sum, sys_full, rtol=1e-6, atol=1e-5)
+    c2w2, _ = shards[0]._stage3_weighted(sys_sum, sts[0])
+    torch.testing.assert_close(c2w2, c2w, rtol=1e-5, atol=1e-5)
+    assert est.enable_cuda_graphs(imgs, masks)
+    c2w_g, _ = est.query_batch(imgs, masks)
+    torch.testing.assert_close(c2w_g, c2w, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("stored_deg,active_deg", [(0, 0), (1, 1), (2, 2), (3, 1), (3, 3)])
+def test_ray_colours_for_low_sh_degrees(sx, synthetic, oracle, stored_deg, active_deg):
+    """SH features are [N, (deg+1)^2, 3]; the fill kernel must stride by the STORED coefficient
+    count and evaluate the ACTIVE degree (reference: get_features + eval_sh(active_sh_degree), sampling.py:116-124,236-251)"""
+    sc = synthetic.synth_scene(150, seed=31)
+    nc = (stored_deg + 1) ** 2
+    sc["features_rest"] = sc["features_rest"][:, :nc - 1].contiguous()
+    sc["sh_degree"] = active_deg
+    scene = sx.GaussianScene.from_dict(sc, device="cuda")
+    assert scene.max_sh_degree == stored_deg and scene.get_features.shape[1] == nc
+    valid = oracle.mask_degraded_ellipsoids(*torch.exp(sc["scaling"]).unbind(-1))
+    idx = torch.arange(int(valid.sum()))
+    ori, dirs, rgb = sx.generate_all_possible_rays(scene, ellipsoid_idx=idx)
+    feats = torch.cat((sc["features_dc"], sc["features_rest"]), 1)
+    o_ref, d_ref, c_ref = oracle.generate_rays(sc["xyz"], sc["scaling"], sc["rotation"], feats, sh_degree=active_deg,
+                                               ellipsoid_idx=idx)
+    assert ori.shape[0] == o_ref.shape[0]
+    # colour of OUR rays evaluated by the oracle's SH on our directions: isolates the SH stage from cell-level flips
+    frac = ((rgb.cpu() - c_ref).abs().max(dim=1).values <= 1e-5).float().mean().item()
+    assert frac >= 0.985, frac
+    with pytest.raises(ValueError):
+        sx.GaussianScene(sc["xyz"], sc["scaling"], sc["rotation"], sc["features_dc"], sc["features_rest"], sh_degree=stored_deg + 1)

@@ -101,7 +101,34 @@ class OracleBatchBackend(OracleBackend):
         return out
 
 
-def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=False, multi_query=False):
+    # all-ray weighted least squares (solve="weighted_ls"): the 13 sums of the pass-2 epilogue and their solve
+    def pass2_batch_ls(self, keys, q, m, z, out, ori, dirs):
+        self.pass2_batch(keys, q, m, z, out)
+        o, d = ori.double(), dirs.double()
+        P = torch.eye(3, dtype=torch.float64)[None] - d[:, :, None] * d[:, None, :]
+        Po = (P @ o[:, :, None])[:, :, 0]
+        sys_ = []
+        for i in range(q.shape[0]):
+            w = out[i].double()
+            R = (w[:, None, None] * P).sum(0)
+            sys_.append(torch.cat((torch.stack((R[0, 0], R[0, 1], R[0, 2], R[1, 1], R[1, 2], R[2, 2])),
+                                   (w[:, None] * Po).sum(0), (w[:, None] * d).sum(0), w.sum()[None])))
+        return out, torch.stack(sys_)
+
+    def ls_solve(self, ls_sys, weight_scale, up):
+        c2w = []
+        for s, u in zip(ls_sys, up):
+            R = torch.stack((s[[0, 1, 2]], s[[1, 3, 4]], s[[2, 4, 5]])) * weight_scale
+            centre = torch.linalg.solve(R, s[6:9] * weight_scale).float()
+            watch = torch.nn.functional.normalize(s[9:12], dim=0).float()
+            out = torch.eye(4)
+            out[:3, :3] = torch.linalg.inv(self.o.make_rotation_mat(-watch, u))
+            out[:3, 3] = centre
+            c2w.append(out)
+        return torch.stack(c2w), torch.zeros(len(c2w), 8)
+
+
+def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=False, multi_query=False, solve="topk"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -122,7 +149,7 @@ def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=Fal
     cache = sx.RayKeyCache(keys, hi - lo, ())
     be = (OracleBatchBackend if multi_query else OracleBackend)(oracle, w, g["tok_pe"], g["up"])
     est = sx.ShardedPoseEstimator(None, ori[lo:hi].contiguous(), dirs[lo:hi].contiguous(), cache, rank, world, backend=be,
-                                  front_end=front_end, multi_query=multi_query)
+                                  front_end=front_end, multi_query=multi_query, solve=solve)
     imgs = torch.arange(nb, dtype=torch.float32)[:, None, None, None].expand(nb, 2, 2, 3).contiguous()
     masks = torch.ones(nb, 2, 2, dtype=torch.bool)
     if local:  # hand over this rank's images only
@@ -167,6 +194,28 @@ def test_two_rank_sharded_query_matches_single_process(oracle, synthetic, tmp_pa
         assert not torch.allclose(c2w[i], c2w[0])
 
 
+@pytest.mark.timeout(300)
+def test_two_rank_weighted_least_squares_one_allreduce(oracle, synthetic, tmp_path):
+    """solve="weighted_ls": each rank accumulates the weighted LS system of ITS rays (weights = its scores), one
+    all-reduce sums the two 13-double systems, every rank solves -> the unsharded oracle's all-ray weighted LS
+    (least_squared_loss.py:62-64: compute_line_intersection_impl2(ori, -dir, score / n_img)) and watch direction"""
+    from conftest import load_golden
+    out = str(tmp_path / "c2w.pt")
+    nb = 3
+    mp.spawn(_worker, args=(2, _free_port(), out, nb, "replicated", False, True, "weighted_ls"), nprocs=2, join=True)
+    c2w = torch.load(out)
+    g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
+    w = synthetic.synth_id_weights(seed=g["weight_seed"])
+    fea = oracle.ray_features(r["ori"], r["dirs"], r["rgb"], w)
+    for i in range(nb):
+        score, _ = oracle.attention_scores(g["tok_pe"] * (1.0 + 0.05 * i), fea, w, return_map=False)
+        wts = score / 256
+        centre = oracle.line_intersection(r["ori"], -r["dirs"], wts)
+        watch = torch.nn.functional.normalize((wts[:, None] * r["dirs"]).sum(0), dim=0)
+        torch.testing.assert_close(c2w[i, :3, 3], centre, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(c2w[i, :3, :3], torch.linalg.inv(oracle.make_rotation_mat(-watch, g["up"])), rtol=1e-4, atol=1e-4)
+
+
 def test_single_rank_path_uses_no_collective(sx, oracle, synthetic):
     from conftest import load_golden
     g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
@@ -182,5 +231,7 @@ def test_single_rank_path_uses_no_collective(sx, oracle, synthetic):
         sx.ShardedPoseEstimator(None, r["ori"], r["dirs"], est.cache, 0, 1, backend=est.backend, front_end="rank0")
     with pytest.raises(ValueError):  # the batched sweep exists on the tensor-core path only
         sx.ShardedPoseEstimator(None, r["ori"], r["dirs"], est.cache, 0, 1, backend=est.backend, multi_query=True)
+    with pytest.raises(ValueError):  # ... and so does the fused weighted least squares
+        sx.ShardedPoseEstimator(None, r["ori"], r["dirs"], est.cache, 0, 1, backend=est.backend, solve="weighted_ls")
     ref, _ = oracle.pose_tail(g["topk_idx"], g["topk_vals"], r["ori"], r["dirs"], g["up"])
     torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
