@@ -39,6 +39,8 @@ _SIGNATURES = {
     "sixdgs_exclusive_scan": ([c_p, c_i64, c_p, c_p], c_i),
     "sixdgs_ray_features_workspace": ([c_i64], c_sz),
     "sixdgs_ray_features": ([c_p, c_p, c_p, c_i64] + [c_p] * 10 + [c_p, c_i, c_p, c_i, c_p, c_sz, c_p], c_i),
+    "sixdgs_ray_features_x2_workspace": ([c_i64], c_sz),
+    "sixdgs_ray_features_x2": ([c_p, c_p, c_p, c_i64] + [c_p] * 10 + [c_p, c_p, c_p, c_sz, c_p], c_i),
     "sixdgs_linear": ([c_p, c_i64, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_i, c_p], c_i),
     "sixdgs_score_parts": ([c_i], c_i),
     "sixdgs_score_workspace": ([c_i], c_sz),

@@ -21,6 +21,7 @@ SOURCES = {
     "knn_grid.cu": ["-fmad=false"],
     "features.cu": [],
     "features_tc.cu": [],
+    "features_x2.cu": [],
     "score_simt.cu": [],
     "score_tc.cu": [],
     "score_tc_mq.cu": [],

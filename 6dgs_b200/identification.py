@@ -167,17 +167,21 @@ class IdentificationModule(torch.nn.Module):
     def build_key_cache(self, rays_ori, rays_dir, rays_rgb) -> RayKeyCache:
         """rays -> PE -> MLP -> k_proj -> K (once per scene / weight update; the reference redoes this per query)."""
         if self.score_impl == "tc_f16x2":
-            # exact mode: fp32 FMA GEMMs (the TF32 build is only good to 1.5e-3 on the keys), staged through fp32 chunks
-            # and split into fp16 hi | lo rows
+            # exact mode (the TF32 build is only good to 1.5e-3 on the keys): three-term split-fp16 tensor-core GEMMs
+            # (csrc/features_x2.cu); SIXDGS_FEATURES_IMPL=simt keeps the fp32 FMA GEMMs, staged through fp32 chunks and
+            # split into fp16 hi | lo rows (the cross-check of the tensor-core build)
             n = rays_ori.shape[0]
             keys = torch.empty(n, 2 * 384, dtype=torch.float16, device=rays_ori.device)
             absmax = torch.zeros(1, dtype=torch.float32, device=rays_ori.device)
             pw = self.packed_weights()
-            for lo in range(0, n, self.SPLIT_CHUNK):
-                hi = min(n, lo + self.SPLIT_CHUNK)
-                kf, _ = ops.ray_features(rays_ori[lo:hi], rays_dir[lo:hi], rays_rgb[lo:hi], pw, k_dtype=F32,
-                                         impl=ops.FEATURES_SIMT)
-                ops.split_keys(kf, keys[lo:hi], absmax)
+            if self.features_impl != "simt":
+                ops.ray_features_x2(rays_ori, rays_dir, rays_rgb, pw, keys, absmax)
+            else:
+                for lo in range(0, n, self.SPLIT_CHUNK):
+                    hi = min(n, lo + self.SPLIT_CHUNK)
+                    kf, _ = ops.ray_features(rays_ori[lo:hi], rays_dir[lo:hi], rays_rgb[lo:hi], pw, k_dtype=F32,
+                                             impl=ops.FEATURES_SIMT)
+                    ops.split_keys(kf, keys[lo:hi], absmax)
             if n and not float(absmax.item()) < ops.F16_MAX:  # one host read per scene build
                 raise SixdgsError(f"f16x2 key cache: max |16 k| = {float(absmax.item()):.4g} exceeds the fp16 range; "
                                   "use score_impl='simt_fp32' for keys of this magnitude")

@@ -155,6 +155,22 @@ def pack_ray_mlp_weights(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch
     }
     for k in ("w1p", "w2", "w3p", "w4", "wk"):
         pw[k + "_tf32"] = tf32(pw[k])
+
+    def x2(t, kpad):
+        """[n,k] fp32 -> [n, 2*kpad] fp16 = [hi | lo] (zero padded): the operand format of the exact tensor-core build"""
+        wpad = torch.zeros(t.shape[0], kpad, device=device)
+        wpad[:, :t.shape[1]] = t
+        hi = wpad.to(torch.float16)
+        lo = (wpad - hi.float()).to(torch.float16)
+        return torch.cat((hi, lo), 1).contiguous()
+
+    w3x = torch.zeros(512, 704, device=device)  # [h 512 | x 141 -> 192]
+    w3x[:, :653] = g("ray_preprocessor.mlp2.0.weight")
+    pw["w1_x2"] = x2(g("ray_preprocessor.mlp.0.weight"), 192)
+    pw["w2_x2"] = x2(pw["w2"], 512)
+    pw["w3_x2"] = x2(w3x, 704)
+    pw["w4_x2"] = x2(pw["w4"], 512)
+    pw["wk_x2"] = x2(pw["wk"], 384)
     return pw
 
 
@@ -184,6 +200,24 @@ def ray_features(ori, dirs, rgb, pw: Dict[str, torch.Tensor], k_dtype: Optional[
          dptr(k_out, None), k_dtype if k_dtype is not None else F32, dptr(feat), impl, dptr(ws, torch.uint8), wsz,
          stream_ptr())
     return k_out, feat
+
+
+def ray_features_x2(ori, dirs, rgb, pw: Dict[str, torch.Tensor], out: Optional[torch.Tensor] = None,
+                    absmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rays -> f16x2 key cache [n,768] on the exact tensor-core path (three-term split-fp16 GEMMs, csrc/features_x2.cu)"""
+    ori, dirs, rgb = f32c(ori), f32c(dirs), f32c(rgb)
+    n = ori.shape[0]
+    if out is None:
+        out = torch.empty(n, 2 * FEAT, dtype=torch.float16, device=ori.device)
+    if n == 0:
+        return out
+    wsz = int(_lib.load().sixdgs_ray_features_x2_workspace(n))
+    ws = torch.empty(wsz, dtype=torch.uint8, device=ori.device)
+    h = torch.float16
+    call("sixdgs_ray_features_x2", dptr(ori), dptr(dirs), dptr(rgb), n, dptr(pw["w1_x2"], h), dptr(pw["b1"]),
+         dptr(pw["w2_x2"], h), dptr(pw["b2"]), dptr(pw["w3_x2"], h), dptr(pw["b3"]), dptr(pw["w4_x2"], h), dptr(pw["b4"]),
+         dptr(pw["wk_x2"], h), dptr(pw["bk"]), dptr(out, h), dptr(absmax), dptr(ws, torch.uint8), wsz, stream_ptr())
+    return out
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = False) -> torch.Tensor:

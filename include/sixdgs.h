@@ -115,6 +115,18 @@ int sixdgs_ray_features(const float* ori, const float* dir, const float* rgb, in
                         const float* wk, const float* bk, void* k_out, int k_dtype, float* feat_out,
                         int impl, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Exact tensor-core build of a SIXDGS_F16X2 key cache: the same five layers as three-term split-fp16 tcgen05 GEMMs
+ * (every activation and weight carried as an fp16 pair hi + lo; fp32-grade keys, ~6x faster than impl 0).
+ * Weights in "x2" layout, a row of width W stored as [hi(W) | lo(W)] fp16 with hi = fp16(w), lo = fp16(w - hi):
+ *   w1 [512, 2*192] (mlp.0, 141 -> 192 zero padded), w2 [512, 2*512], w3 [512, 2*704] (mlp2.0: [h 512 | x 141 -> 192]),
+ *   w4 [384, 2*512], wk [384, 2*384]; biases fp32.  k_out [n, 768] fp16; absmax as in sixdgs_split_keys (nullable).
+ * workspace >= sixdgs_ray_features_x2_workspace(n) bytes. */
+size_t sixdgs_ray_features_x2_workspace(int64_t n);
+int sixdgs_ray_features_x2(const float* ori, const float* dir, const float* rgb, int64_t n, const void* w1,
+                           const float* b1, const void* w2, const float* b2, const void* w3, const float* b3,
+                           const void* w4, const float* b4, const void* wk, const float* bk, void* k_out,
+                           float* absmax, void* workspace, size_t workspace_bytes, void* stream);
+
 /* generic y[m,n] = act(x[m,k] w[n,k]^T + b[n]); k % 16 == 0, lda/ldc in elements (used for q_proj,
  * our_multihead_attention.py:74, with img features padded 398 -> 400). */
 int sixdgs_linear(const float* x, int64_t m, int k, int lda, const float* w, const float* b, int n,

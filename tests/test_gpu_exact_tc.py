@@ -251,3 +251,49 @@ def test_full_size_1m_gaussians_every_score_vs_fp64(sx, synthetic):
         c2w, _ = sx.ops.pose_tail(ori, dirs, idx, vals, up)
         c2w_ref, _ = sx.ops.pose_tail(ori, dirs, rt.indices, rt.values.float(), up)
         torch.testing.assert_close(c2w, c2w_ref, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------ exact tensor-core key build
+@pytest.mark.parametrize("n", [1, 127, 129, 5513, 300_001])
+def test_exact_tensor_core_key_build_vs_fp64(sx, synthetic, n):
+    """csrc/features_x2.cu (three-term split-fp16 GEMMs for the five MLP layers) against an fp64 evaluation of the
+    same layers: the f16x2 keys must be fp32-grade (as good as the fp32 FMA build), row counts around the 128-row tile
+    and across the 131072-row workspace chunk"""
+    from importlib import import_module
+    F32 = import_module("6dgs_b200._lib").F32
+    idm = make_module(sx, synthetic, "tc_f16x2")
+    gen = torch.Generator().manual_seed(n)
+    ori = (torch.randn(n, 3, generator=gen) * 3).to(DEV)
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1).to(DEV)
+    rgb = torch.rand(n, 3, generator=gen).to(DEV)
+    pw = idm.packed_weights()
+
+    def pe(p, nf):
+        ang = (p[..., None] * (2.0 ** torch.arange(nf, device=p.device, dtype=p.dtype))).reshape(p.shape[0], -1)
+        return torch.cat((torch.sin(ang), torch.cos(ang)), -1)
+
+    sd = {k: v.double() for k, v in idm.state_dict().items()}
+    x = torch.cat((ori, dirs, rgb, pe(ori, 8), pe(dirs, 8), pe(rgb, 6)), -1).double()
+    lin = torch.nn.functional.linear
+    h = torch.relu(lin(torch.relu(lin(x, sd["ray_preprocessor.mlp.0.weight"], sd["ray_preprocessor.mlp.0.bias"])),
+                       sd["ray_preprocessor.mlp.2.weight"], sd["ray_preprocessor.mlp.2.bias"]))
+    f = lin(torch.relu(lin(torch.cat((h, x), -1), sd["ray_preprocessor.mlp2.0.weight"], sd["ray_preprocessor.mlp2.0.bias"])),
+            sd["ray_preprocessor.mlp2.2.weight"], sd["ray_preprocessor.mlp2.2.bias"])
+    ref = lin(f, sd["attention.k_proj.weight"], sd["attention.k_proj.bias"])
+    absmax = torch.zeros(1, device=DEV)
+    keys = sx.ops.ray_features_x2(ori, dirs, rgb, pw, absmax=absmax)
+    rec = (keys[:, :384].double() + keys[:, 384:].double()) / 16.0
+    kf, _ = sx.ops.ray_features(ori, dirs, rgb, pw, k_dtype=F32, impl=sx.ops.FEATURES_SIMT)
+    scale = ref.abs().max().item()
+    e_x2 = (rec - ref).abs().max().item() / scale
+    e_f32 = (kf.double() - ref).abs().max().item() / scale
+    report(f"exact key build, {n} rays: max err / max|k| of the split-fp16 tensor-core build {e_x2:.2e}, of the fp32 FMA build {e_f32:.2e}")
+    assert e_x2 < 3e-6 and e_x2 < 5 * e_f32 + 5e-7, (e_x2, e_f32)
+    assert abs(absmax.item() - 16.0 * rec.abs().max().item()) <= 1e-3 * absmax.item()
+    # the module's cache builder takes this path by default and the SIMT + split path on request: same keys to fp32 grade
+    cache = idm.build_key_cache(ori, dirs, rgb)
+    assert torch.equal(cache.keys, keys)
+    idm.features_impl = "simt"
+    c2 = idm.build_key_cache(ori, dirs, rgb)
+    r2 = (c2.keys[:, :384].double() + c2.keys[:, 384:].double()) / 16.0
+    assert (r2 - rec).abs().max().item() / scale < 5e-6
