@@ -180,6 +180,20 @@ def gen_id_module_peaked(ori, dirs, rgb, q_gain=20.0):
         R=R, T=T, pred_c2w=np.array(results[0]["pred_c2w"], dtype=np.float32))
 
 
+def gen_ply():
+    """point_cloud.ply written by the reference's OWN save_ply (scene/gaussian_model.py:298-332: attribute order from
+    construct_list_of_attributes :284-296, SH coefficients transposed to channel-major) through the plyfile-format shim
+    of oracle/ref_shims.py; the tensors it was written from are stored next to it."""
+    sc = synthetic.synth_scene(96, seed=41)
+    gm = ref_model(sc)
+    gm._opacity = torch.randn(96, 1, generator=torch.Generator().manual_seed(42))
+    path = os.path.join(OUT, "point_cloud_ref.ply")
+    gm.save_ply(path)
+    npz("ply_ref.npz", xyz=sc["xyz"], scaling=sc["scaling"], rotation=sc["rotation"], features_dc=sc["features_dc"],
+        features_rest=sc["features_rest"], opacity=gm._opacity, attributes=np.array(gm.construct_list_of_attributes()))
+    print(f"point_cloud_ref.ply: {os.path.getsize(path)} bytes")
+
+
 def gen_line_intersection():
     g = torch.Generator().manual_seed(21)
     cases = {}
@@ -231,6 +245,9 @@ def gen_pose(idm, ori, dirs, rgb):
 
 
 if __name__ == "__main__":
+    if "--only-ply" in sys.argv:
+        gen_ply()
+        sys.exit(0)
     if "--only-peaked" in sys.argv:  # add the peaked-softmax fixture without touching the others (rays from the fixture)
         g = np.load(os.path.join(OUT, "rays_small.npz"))
         gen_id_module_peaked(*(torch.from_numpy(g[k]) for k in ("ori", "dirs", "rgb")))
@@ -246,4 +263,5 @@ if __name__ == "__main__":
     gen_id_module_peaked(ori, dirs, rgb)
     gen_line_intersection()
     gen_pose(idm, ori, dirs, rgb)
+    gen_ply()
     os.system(f"du -sh {OUT}")

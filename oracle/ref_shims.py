@@ -14,6 +14,36 @@ import torch
 REFERENCE_ROOT = "/root/reference"
 
 
+class _PlyElement:
+    """The two plyfile calls scene/gaussian_model.py:save_ply makes (:331-332), writing what plyfile writes for a
+    structured float32 array: `element <name> <count>` + one `property float <field>` line per field, then the packed
+    little-endian records.  (plyfile itself is not installed in the build container.)"""
+
+    def __init__(self, data, name):
+        self.data, self.name = data, name
+
+    @staticmethod
+    def describe(data, name):
+        assert all(data.dtype[f].str in ("<f4", "=f4") for f in data.dtype.names), "save_ply only writes f4 fields"
+        return _PlyElement(data, name)
+
+
+class _PlyData:
+    def __init__(self, elements):
+        self.elements = list(elements)
+
+    def write(self, path):
+        with open(path, "wb") as fh:
+            fh.write(b"ply\nformat binary_little_endian 1.0\n")
+            for el in self.elements:
+                fh.write(f"element {el.name} {len(el.data)}\n".encode("ascii"))
+                for f in el.data.dtype.names:
+                    fh.write(f"property float {f}\n".encode("ascii"))
+            fh.write(b"end_header\n")
+            for el in self.elements:
+                fh.write(el.data.astype(el.data.dtype.newbyteorder("<")).tobytes())
+
+
 def install(backbone_factory=None):
     """``backbone_factory()`` must return a module exposing ``forward_features`` (default: the
     product package's SyntheticBackbone so reference and product see the same fake features)."""
@@ -21,8 +51,8 @@ def install(backbone_factory=None):
         sys.path.insert(0, REFERENCE_ROOT)
     if "plyfile" not in sys.modules:
         m = types.ModuleType("plyfile")
-        m.PlyData = object
-        m.PlyElement = object
+        m.PlyData = _PlyData
+        m.PlyElement = _PlyElement
         sys.modules["plyfile"] = m
     if "simple_knn" not in sys.modules:
         pkg = types.ModuleType("simple_knn")

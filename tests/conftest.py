@@ -33,7 +33,7 @@ def pytest_sessionstart(session):
 
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name))
-    return {k: (torch.from_numpy(z[k]) if z[k].ndim else z[k].item()) for k in z.files}
+    return {k: ((torch.from_numpy(z[k]) if z[k].dtype.kind in "fiub" else z[k]) if z[k].ndim else z[k].item()) for k in z.files}
 
 
 @pytest.fixture(scope="session")

@@ -121,6 +121,28 @@ def test_ply_loader_roundtrip(sx, synthetic, tmp_path):
     torch.testing.assert_close(scene.get_scaling, torch.exp(sc["scaling"]))
 
 
+def test_ply_loader_reads_the_file_written_by_the_reference_save_ply(sx):
+    """tests/golden/point_cloud_ref.ply was written by the reference's own GaussianModel.save_ply
+    (scene/gaussian_model.py:298-332, attribute order :284-296) from the tensors in ply_ref.npz (oracle/gen_golden.py
+    --only-ply): load_ply must give those tensors back bit for bit, in the layout get_features returns"""
+    import os
+    from conftest import GOLDEN, load_golden
+    g = load_golden("ply_ref.npz")
+    scene = sx.GaussianScene.load_ply(os.path.join(GOLDEN, "point_cloud_ref.ply"), device="cpu")
+    assert scene.active_sh_degree == 3 and scene.max_sh_degree == 3
+    assert torch.equal(scene.get_xyz, g["xyz"])
+    assert torch.equal(scene._scaling, g["scaling"]) and torch.equal(scene._rotation, g["rotation"])
+    assert torch.equal(scene.get_features, torch.cat((g["features_dc"], g["features_rest"]), 1))
+    torch.testing.assert_close(scene.get_scaling, torch.exp(g["scaling"]))
+    # the header is the reference's attribute list in the reference's order
+    with open(os.path.join(GOLDEN, "point_cloud_ref.ply"), "rb") as fh:
+        head = fh.read(4096).split(b"end_header")[0].decode("ascii").splitlines()
+    props = [ln.split()[-1] for ln in head if ln.startswith("property")]
+    assert props[:6] == ["x", "y", "z", "nx", "ny", "nz"] and props[6:9] == ["f_dc_0", "f_dc_1", "f_dc_2"]
+    assert props[9:54] == [f"f_rest_{i}" for i in range(45)] and props[54] == "opacity"
+    assert props[55:] == ["scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"]
+
+
 def test_training_mode_refuses_cpu_tensors(sx, synthetic):
     """with gradients enabled forward() takes the differentiable torch-op route, which is CUDA-only like the rest"""
     idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone())

@@ -268,3 +268,17 @@ def test_ray_colours_for_low_sh_degrees(sx, synthetic, oracle, stored_deg, activ
     assert frac >= 0.985, frac
     with pytest.raises(ValueError):
         sx.GaussianScene(sc["xyz"], sc["scaling"], sc["rotation"], sc["features_dc"], sc["features_rest"], sh_degree=stored_deg + 1)
+
+
+def test_scene_loaded_from_the_reference_ply_generates_the_same_rays(sx, synthetic):
+    """PLY written by the reference's save_ply -> load_ply -> rays == rays of the scene built from the same tensors"""
+    import os
+    from conftest import GOLDEN, load_golden
+    g = load_golden("ply_ref.npz")
+    a = sx.GaussianScene.load_ply(os.path.join(GOLDEN, "point_cloud_ref.ply"), device="cuda")
+    b = sx.GaussianScene(g["xyz"], g["scaling"], g["rotation"], g["features_dc"], g["features_rest"], 3, device="cuda")
+    ra = sx.generate_all_possible_rays(a, max_ellipsoids=None)
+    rb = sx.generate_all_possible_rays(b, max_ellipsoids=None)
+    assert ra[0].shape[0] > 1000
+    for x, y in zip(ra, rb):
+        assert torch.equal(x, y)
