@@ -51,8 +51,9 @@ class DinoV2ViTS14(torch.nn.Module):
     """ViT-S/14 with DINOv2's parameter names (cls_token, pos_embed[1,1+37*37,384], patch_embed.proj,
     blocks.N.{norm1,attn.qkv,attn.proj,ls1.gamma,norm2,mlp.fc1,mlp.fc2,ls2.gamma}, norm)."""
 
-    def __init__(self, dim=384, depth=12, heads=6, patch=14, base_grid=37):
+    def __init__(self, dim=384, depth=12, heads=6, patch=14, base_grid=37, interpolate_offset=0.1):
         super().__init__()
+        self.interpolate_offset = interpolate_offset  # hub value for dinov2_vits14; 0 / None = resample to an exact size
         self.patch_embed = torch.nn.Module()
         self.patch_embed.proj = torch.nn.Conv2d(3, dim, patch, patch)
         self.cls_token = torch.nn.Parameter(torch.zeros(1, 1, dim))
@@ -72,7 +73,15 @@ class DinoV2ViTS14(torch.nn.Module):
         if self._pos_cache is None or self._pos_cache[0] != key or torch.is_grad_enabled() and self.pos_embed.requires_grad:
             cls, grid = self.pos_embed[:, :1], self.pos_embed[:, 1:]
             g = grid.reshape(1, self.base_grid, self.base_grid, -1).permute(0, 3, 1, 2)
-            g = F.interpolate(g, size=(gh, gw), mode="bicubic", align_corners=False)
+            if self.interpolate_offset:
+                # the torch.hub dinov2_vits14 the reference loads (backbone.py:15) is built with interpolate_offset=0.1,
+                # interpolate_antialias=False: the table is resampled by SCALE FACTOR (g + 0.1) / 37, not to a size --
+                # bicubic with a scale factor samples at slightly different source coordinates than size=(g, g)
+                sf = ((gh + self.interpolate_offset) / self.base_grid, (gw + self.interpolate_offset) / self.base_grid)
+                g = F.interpolate(g, scale_factor=sf, mode="bicubic", align_corners=False)
+                assert g.shape[-2:] == (gh, gw)
+            else:
+                g = F.interpolate(g, size=(gh, gw), mode="bicubic", align_corners=False)
             pos = torch.cat((cls, g.permute(0, 2, 3, 1).reshape(1, gh * gw, -1)), 1)
             if torch.is_grad_enabled() and self.pos_embed.requires_grad:
                 return pos

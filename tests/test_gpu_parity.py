@@ -99,15 +99,31 @@ def _scene_from_golden(sx, g):
     return sx.GaussianScene(g["xyz"], g["scaling"], g["rotation"], g["features_dc"], g["features_rest"], 3, device=DEV)
 
 
-def test_generate_rays_vs_reference(sx):
+def _rays_of_matching_ellipsoids(gid, gid_ref, n_ell, min_match):
+    """Rays are emitted ellipsoid-major in the same ellipsoid order on both sides; a flipped discrete decision changes
+    the ray COUNT of one ellipsoid and would shift every later ray.  Align per ellipsoid instead: keep the rays of the
+    ellipsoids whose counts agree (must be >= min_match of them) -> boolean masks over (mine, reference)."""
+    cnt = torch.bincount(gid, minlength=n_ell)
+    cnt_ref = torch.bincount(gid_ref, minlength=n_ell)
+    same = cnt == cnt_ref
+    frac = same[(cnt + cnt_ref) > 0].float().mean().item()
+    assert frac >= min_match, f"only {frac:.4f} of the ellipsoids have the reference ray count"
+    return same[gid], same[gid_ref]
+
+
+def test_generate_rays_vs_reference(sx, oracle):
     g = load_golden("rays_small.npz")
     scene = _scene_from_golden(sx, g)
-    ori, dirs, rgb = sx.generate_all_possible_rays(scene, ellipsoid_idx=g["perm"])
+    ori, dirs, rgb, gid = sx.generate_all_possible_rays(scene, ellipsoid_idx=g["perm"], return_ids=True)
     assert abs(ori.shape[0] - g["ori"].shape[0]) <= 3
-    if ori.shape[0] == g["ori"].shape[0]:
-        for mine, ref, tol in ((ori, g["ori"], 1e-5), (dirs, g["dirs"], 1e-5), (rgb, g["rgb"], 1e-5)):
-            frac = ((mine.cpu() - ref).abs().max(dim=1).values <= tol).float().mean().item()
-            assert frac >= 0.985, frac
+    # the fixture stores no ellipsoid ids; the oracle (pinned bit-exact to this fixture) supplies them
+    feats = torch.cat((g["features_dc"], g["features_rest"]), 1)
+    o_ori, _, _, aux = oracle.generate_rays(g["xyz"], g["scaling"], g["rotation"], feats, ellipsoid_idx=g["perm"], return_aux=True)
+    assert torch.equal(o_ori, g["ori"])
+    km, kr = _rays_of_matching_ellipsoids(gid.cpu(), aux["gid"], g["xyz"].shape[0], 0.98)
+    for mine, ref, tol in ((ori, g["ori"], 1e-5), (dirs, g["dirs"], 1e-5), (rgb, g["rgb"], 1e-5)):
+        frac = ((mine.cpu()[km] - ref[kr]).abs().max(dim=1).values <= tol).float().mean().item()
+        assert frac >= 0.985, frac
     assert torch.allclose(dirs.norm(dim=1), torch.ones_like(dirs[:, 0]), atol=1e-5)
     assert (rgb >= 0).all()
 
@@ -464,11 +480,11 @@ def test_heavy_tailed_scene_ray_counts_vs_oracle(sx, synthetic, oracle):
                                                 ellipsoid_idx=perm, return_aux=True)
     cnt = torch.bincount(gid.cpu(), minlength=400)
     cnt_ref = torch.bincount(aux["gid"], minlength=400)
-    assert (cnt == cnt_ref).float().mean().item() >= 0.97
     assert abs(int(cnt.sum()) - int(cnt_ref.sum())) <= 0.01 * int(cnt_ref.sum())
-    if ori.shape[0] == o_ori.shape[0]:
-        frac = ((ori.cpu() - o_ori).abs().max(dim=1).values <= 1e-5 * (1 + o_ori.abs().max(dim=1).values)).float().mean().item()
-        assert frac >= 0.97
+    km, kr = _rays_of_matching_ellipsoids(gid.cpu(), aux["gid"], 400, 0.97)
+    a, b = ori.cpu()[km], o_ori[kr]
+    frac = ((a - b).abs().max(dim=1).values <= 1e-5 * (1 + b.abs().max(dim=1).values)).float().mean().item()
+    assert frac >= 0.97, frac
 
 
 def test_training_mode_forward_is_differentiable_and_matches_kernels(sx, synthetic):
