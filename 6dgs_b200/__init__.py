@@ -23,7 +23,7 @@ from .sharding import CudaBackend, ShardedPoseEstimator  # noqa: F401
 
 test_pose_estimation.__test__ = False  # not a pytest test despite the reference's name
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 # make `import sixdgs_b200.<sub>` resolve to the same module objects
 for _name, _mod in list(_sys.modules.items()):

@@ -1,0 +1,152 @@
+"""Offline evaluation driver: the evaluation half of the reference's ``pretrain_eval_attention.py`` (:31-154,200-248)
+without its network / ANTLR dependencies.
+
+The reference driver discovers ``point_cloud/iteration_*/point_cloud.ply`` under an experiment directory
+(``pose_estimation/file_utils.py:19-72``), re-parses ``cfg_args`` with an ANTLR-3 grammar that no longer loads,
+re-reads the dataset, downloads DINOv2 through torch.hub, fits the identification module, explores the model and runs
+``test_pose_estimation`` twice.  Here everything a 3DGS experiment directory already contains is enough:
+
+    <exp>/point_cloud/iteration_<N>/point_cloud.ply     the scene (highest iteration wins, like the reference)
+    <exp>/cameras.json                                  3DGS camera dump (id, img_name, width, height, position,
+                                                        rotation, fx, fy -- scene/__init__.py / utils/camera_utils.py)
+    <exp>/id_module.th                                  optional: {"model_state_dict": ...} (pose_estimation/train.py:309-317)
+    <images>/<img_name>.{png,jpg,jpeg}                  the query images (RGBA alpha is composited like test.py:69-83)
+
+    python tools/eval_pose.py --exp_path <exp> --images <dir> --out results.json [--dinov2 vits14.pth]
+
+Training is out of scope: without ``id_module.th`` the module is randomly initialised and the poses are
+meaningless -- the driver says so and still runs (smoke / timing use).  Output: the reference's JSON schema
+(list of per-frame dicts with pred_c2w / gt_c2w, test.py:290-302) plus the two averages.
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import json
+import math
+import os
+import re
+from collections import namedtuple
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+CameraInfo = namedtuple("CameraInfo", "uid R T FovY FovX image image_path image_name width height")
+
+
+def find_point_cloud(exp_path: str) -> str:
+    """highest ``iteration_<N>`` under <exp>/point_cloud (reference file_utils.py:46-72 picks the last checkpoint)"""
+    cands = glob.glob(os.path.join(exp_path, "point_cloud", "iteration_*", "point_cloud.ply"))
+    if not cands:
+        raise FileNotFoundError(f"no point_cloud/iteration_*/point_cloud.ply under {exp_path}")
+    return max(cands, key=lambda p: int(re.search(r"iteration_(\d+)", p).group(1)))
+
+
+def focal2fov(focal: float, pixels: float) -> float:
+    return 2.0 * math.atan(pixels / (2.0 * focal))
+
+
+def cameras_from_json(path: str, image_dir: Optional[str], every: int = 1, load_images: bool = True) -> List[CameraInfo]:
+    """3DGS ``cameras.json`` -> CameraInfo list.  The dump stores the camera-to-world rotation and the camera position
+    (utils/camera_utils.py:camera_to_JSON); CameraInfo keeps R = c2w rotation and T = w2c translation = -R^T pos
+    (scene/dataset_readers.py), which is what test.py:47-67 turns back into a pose."""
+    from PIL import Image
+
+    cams = []
+    for i, c in enumerate(json.load(open(path))):
+        if i % every:
+            continue
+        R = np.asarray(c["rotation"], dtype=np.float32)
+        pos = np.asarray(c["position"], dtype=np.float32)
+        T = (-R.T @ pos).astype(np.float32)
+        w, h = int(c["width"]), int(c["height"])
+        img, img_path = None, ""
+        if load_images:
+            if image_dir is None:
+                raise ValueError("--images is required to load the query images")
+            for ext in ("", ".png", ".jpg", ".jpeg", ".JPG", ".PNG"):
+                p = os.path.join(image_dir, c["img_name"] + ext)
+                if os.path.isfile(p):
+                    img_path = p
+                    break
+            if not img_path:
+                raise FileNotFoundError(f"image {c['img_name']} not found in {image_dir}")
+            img = np.array(Image.open(img_path))
+            if img.ndim == 2:
+                img = np.repeat(img[..., None], 3, axis=-1)
+            h, w = img.shape[:2]
+        cams.append(CameraInfo(int(c.get("id", i)), R, T, np.float32(focal2fov(c["fy"], c["height"])),
+                               np.float32(focal2fov(c["fx"], c["width"])), img, img_path, c["img_name"], w, h))
+    return cams
+
+
+def model_up_from_cameras(cams: List[CameraInfo]) -> np.ndarray:
+    """mean of the cameras' R[:3, 1] columns (pretrain_eval_attention.py:91-98)"""
+    return np.mean(np.asarray([c.R[:3, 1] for c in cams], dtype=np.float32), axis=0)
+
+
+def load_id_module(sx, exp_path: Optional[str], weights: Optional[str], score_impl: str, device, backbone=None):
+    idm = sx.IdentificationModule("dino", score_impl=score_impl, backbone=backbone)
+    path = weights or (os.path.join(exp_path, "id_module.th") if exp_path else None)
+    trained = False
+    if path and os.path.exists(path):
+        ckpt = torch.load(path, map_location="cpu")
+        sd = ckpt.get("model_state_dict", ckpt)
+        missing = idm.load_state_dict(sd, strict=False)
+        hot = [k for k in missing.missing_keys if k.startswith(("ray_preprocessor.", "attention.", "camera_direction"))]
+        if hot:
+            raise KeyError(f"{path} lacks hot-path parameters: {hot[:4]} ...")
+        trained = True
+    else:
+        print("[eval_driver] no id_module.th: the identification module is RANDOMLY initialised -- poses are meaningless "
+              "(training is out of scope here; fit it with the reference's train_id_module)")
+    return idm.to(device).eval().requires_grad_(False), trained
+
+
+def main(argv=None):
+    import importlib
+
+    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap.add_argument("--exp_path", help="3DGS experiment directory (point_cloud/, cameras.json, optional id_module.th)")
+    ap.add_argument("--ply", help="explicit point_cloud.ply (overrides --exp_path discovery)")
+    ap.add_argument("--cameras", help="explicit cameras.json")
+    ap.add_argument("--images", help="directory with the query images named by cameras.json:img_name")
+    ap.add_argument("--weights", help="id_module.th (default <exp_path>/id_module.th)")
+    ap.add_argument("--dinov2", help="dinov2_vits14 state dict (sets SIXDGS_DINOV2_WEIGHTS; torch.hub is not reachable offline)")
+    ap.add_argument("--out", default="results.json")
+    ap.add_argument("--every", type=int, default=8, help="test split = every N-th camera (3DGS llffhold convention)")
+    ap.add_argument("--max_ellipsoids", type=int, default=1000, help="1000 = the reference's cap (sampling.py:146-148); 0 = all")
+    ap.add_argument("--score_impl", default="tc_f16x2", choices=["tc_f16x2", "simt_fp32", "tc_bf16"])
+    ap.add_argument("--backbone", default="dino", choices=["dino", "synthetic"],
+                    help="synthetic = the deterministic stand-in used by the fixtures (no DINOv2 weights offline)")
+    ap.add_argument("--seed", type=int, default=55176280)  # pretrain_eval_attention.py:183
+    args = ap.parse_args(argv)
+    if args.dinov2:
+        os.environ["SIXDGS_DINOV2_WEIGHTS"] = args.dinov2
+    sx = importlib.import_module(__package__ or "6dgs_b200")
+    dev = torch.device("cuda")
+    torch.manual_seed(args.seed)
+    ply = args.ply or find_point_cloud(args.exp_path)
+    cams_json = args.cameras or os.path.join(args.exp_path, "cameras.json")
+    scene = sx.GaussianScene.load_ply(ply, device=dev)
+    all_cams = cameras_from_json(cams_json, args.images, every=1, load_images=False)
+    test_cams = cameras_from_json(cams_json, args.images, every=max(1, args.every))
+    model_up = torch.from_numpy(model_up_from_cameras(all_cams)).to(dev)
+    backbone = sx.synthetic.SyntheticBackbone() if args.backbone == "synthetic" else None
+    idm, trained = load_id_module(sx, args.exp_path, args.weights, args.score_impl, dev, backbone)
+    rays = sx.generate_all_possible_rays(scene, sample_quadricell_targets=50,
+                                         max_ellipsoids=None if args.max_ellipsoids == 0 else args.max_ellipsoids)
+    results, t_err, a_err, _, _ = sx.test_pose_estimation(test_cams, idm, *rays, model_up,
+                                                          sequence_id=os.path.basename(os.path.normpath(args.exp_path or ply)))
+    out = {"results": results, "avg_translation_error": t_err, "avg_angular_error": a_err, "n_rays": int(rays[0].shape[0]),
+           "trained_weights": trained, "point_cloud": ply}
+    with open(args.out, "w") as fh:
+        json.dump(out, fh)
+    print(f"[eval_driver] {len(results)} frames, {rays[0].shape[0]} rays -> {args.out}: "
+          f"translation {t_err:.4f}, angular {a_err:.3f} deg")
+    return out
+
+
+if __name__ == "__main__":
+    main()

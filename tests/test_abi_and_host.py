@@ -195,3 +195,88 @@ def test_every_kernel_family_in_the_header_cites_the_reference():
     assert len(blocks) >= 8
     for b in blocks:
         assert re.search(r"\.py:\d+", b) or "our_multihead_attention" in b, b
+
+
+def _write_experiment(tmp_path, synthetic):
+    """a 3DGS-style experiment directory built from the fixtures: PLY in the reference writer's layout, cameras.json in
+    the 3DGS dump convention (c2w rotation + position), PNG images, id_module.th"""
+    import json
+    import shutil
+    from PIL import Image
+    from conftest import GOLDEN, load_golden
+    exp = tmp_path / "exp"
+    for it in (7000, 30000):
+        (exp / "point_cloud" / f"iteration_{it}").mkdir(parents=True)
+        shutil.copy(f"{GOLDEN}/point_cloud_ref.ply", exp / "point_cloud" / f"iteration_{it}" / "point_cloud.ply")
+    p = load_golden("pose.npz")
+    img_dir = tmp_path / "images"
+    img_dir.mkdir()
+    cams = []
+    for i in range(3):
+        R, T = p["R"][i].numpy(), p["T"][i].numpy()
+        pos = -(R @ T)  # T = -R^T pos
+        Image.fromarray(p[f"img{i}"].numpy()).save(img_dir / f"view_{i}.png")
+        f = 64 / (2 * np.tan(0.45))
+        cams.append({"id": i, "img_name": f"view_{i}", "width": 64, "height": 64, "position": pos.tolist(),
+                     "rotation": R.tolist(), "fx": float(f), "fy": float(f)})
+    json.dump(cams, open(exp / "cameras.json", "w"))
+    torch.save({"epoch": 1, "model_state_dict": synthetic.synth_id_weights(seed=3)}, exp / "id_module.th")
+    return exp, img_dir, p
+
+
+def test_eval_driver_host_logic(sx, synthetic, tmp_path):
+    """offline driver (6dgs_b200/eval_driver.py): checkpoint discovery, cameras.json -> CameraInfo (same R / T / FoV the
+    fixtures were generated with), model-up vector"""
+    import importlib
+    drv = importlib.import_module("6dgs_b200.eval_driver")
+    exp, img_dir, p = _write_experiment(tmp_path, synthetic)
+    assert drv.find_point_cloud(str(exp)).endswith("iteration_30000/point_cloud.ply")
+    cams = drv.cameras_from_json(str(exp / "cameras.json"), str(img_dir))
+    assert len(cams) == 3 and cams[1].image.shape == (64, 64, 4) and cams[0].image.shape == (64, 64, 3)
+    for i, c in enumerate(cams):
+        np.testing.assert_allclose(c.R, p["R"][i].numpy(), atol=1e-6)
+        np.testing.assert_allclose(c.T, p["T"][i].numpy(), atol=1e-5)
+        assert abs(float(c.FovX) - 0.9) < 1e-5 and (c.width, c.height) == (64, 64)
+    up = drv.model_up_from_cameras(cams)
+    np.testing.assert_allclose(up, np.mean([p["R"][i].numpy()[:3, 1] for i in range(3)], axis=0), atol=1e-6)
+    with pytest.raises(FileNotFoundError):
+        drv.find_point_cloud(str(tmp_path))
+
+
+def dinov2_vits14_manifest():
+    """parameter names and shapes of the torch.hub ``dinov2_vits14`` state dict the reference loads (backbone.py:15;
+    facebookresearch/dinov2 vision_transformer.py with block_chunks=0: patch 14, dim 384, depth 12, 6 heads, MLP x4,
+    LayerScale, 518/14 = 37x37 position table) -- written out by hand: the checkpoint itself is not fetchable offline"""
+    m = {"cls_token": (1, 1, 384), "pos_embed": (1, 1 + 37 * 37, 384), "mask_token": (1, 384),
+         "patch_embed.proj.weight": (384, 3, 14, 14), "patch_embed.proj.bias": (384,), "norm.weight": (384,), "norm.bias": (384,)}
+    for i in range(12):
+        b = f"blocks.{i}."
+        m.update({b + "norm1.weight": (384,), b + "norm1.bias": (384,), b + "attn.qkv.weight": (1152, 384),
+                  b + "attn.qkv.bias": (1152,), b + "attn.proj.weight": (384, 384), b + "attn.proj.bias": (384,),
+                  b + "ls1.gamma": (384,), b + "norm2.weight": (384,), b + "norm2.bias": (384,),
+                  b + "mlp.fc1.weight": (1536, 384), b + "mlp.fc1.bias": (1536,), b + "mlp.fc2.weight": (384, 1536),
+                  b + "mlp.fc2.bias": (384,), b + "ls2.gamma": (384,)})
+    return m
+
+
+def test_local_vit_is_name_compatible_with_the_dinov2_vits14_checkpoint(sx, tmp_path, monkeypatch):
+    """a real dinov2_vits14 state dict must load into the local ViT with no missing / unexpected key
+    (SIXDGS_DINOV2_WEIGHTS path of create_backbone), and the loaded values must be the ones used"""
+    man = dinov2_vits14_manifest()
+    vit = sx.DinoV2ViTS14()
+    sd = vit.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == man
+    assert sum(int(np.prod(s)) for s in man.values()) == sum(p.numel() for p in vit.parameters())
+    g = torch.Generator().manual_seed(8)
+    fake = {k: torch.randn(*s, generator=g) * 0.02 for k, s in man.items()}
+    path = tmp_path / "dinov2_vits14.pth"
+    torch.save(fake, path)
+    monkeypatch.setenv("SIXDGS_DINOV2_WEIGHTS", str(path))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")  # the "randomly initialised" warning must NOT fire
+        model, wh, nf = sx.create_backbone("dino")
+    assert wh == (16, 16) and nf == 384
+    res = model.load_state_dict(fake, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    torch.testing.assert_close(model.state_dict()["blocks.7.attn.qkv.weight"], fake["blocks.7.attn.qkv.weight"])

@@ -282,3 +282,25 @@ def test_scene_loaded_from_the_reference_ply_generates_the_same_rays(sx, synthet
     assert ra[0].shape[0] > 1000
     for x, y in zip(ra, rb):
         assert torch.equal(x, y)
+
+
+def test_offline_eval_driver_end_to_end(sx, synthetic, tmp_path):
+    """tools/eval_pose.py on a 3DGS-style experiment directory: discovers the PLY written by the reference's save_ply,
+    reads cameras.json / PNGs / id_module.th, runs test_pose_estimation and writes the reference's JSON schema; the ground
+    truth poses are the fixture's (reference test_pose_estimation), the predictions are finite rigid poses"""
+    import importlib
+    import json
+    from test_abi_and_host import _write_experiment
+    drv = importlib.import_module("6dgs_b200.eval_driver")
+    exp, img_dir, p = _write_experiment(tmp_path, synthetic)
+    out = tmp_path / "results.json"
+    res = drv.main(["--exp_path", str(exp), "--images", str(img_dir), "--out", str(out), "--every", "1",
+                    "--backbone", "synthetic", "--max_ellipsoids", "0"])
+    saved = json.load(open(out))
+    assert len(saved["results"]) == 3 and saved["trained_weights"] is True and saved["n_rays"] == res["n_rays"] > 1000
+    gt = torch.tensor([r["gt_c2w"] for r in saved["results"]])
+    torch.testing.assert_close(gt, p["gt_c2w"], rtol=1e-4, atol=1e-4)
+    pred = torch.tensor([r["pred_c2w"] for r in saved["results"]])
+    assert torch.isfinite(pred).all()
+    rot = pred[:, :3, :3]
+    torch.testing.assert_close(rot @ rot.transpose(1, 2), torch.eye(3).expand(3, 3, 3), rtol=1e-3, atol=1e-3)
