@@ -52,6 +52,9 @@ _SIGNATURES = {
     "sixdgs_score_batch_workspace": ([c_i], c_sz),
     "sixdgs_score_pass1_batch": ([c_p, c_i, c_i64, c_p, c_i, c_i, c_p, c_p, c_p, c_sz, c_p], c_i),
     "sixdgs_score_pass2_batch": ([c_p, c_i, c_i64, c_p, c_i, c_i, c_p, c_p, c_p, c_i64, c_p, c_sz, c_p], c_i),
+    "sixdgs_score_backward_parts": ([], c_i),
+    "sixdgs_score_backward_gbar": ([c_p, c_i64, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p], c_i),
+    "sixdgs_score_backward_dlogits": ([c_p, c_i64, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p], c_i),
     "sixdgs_split_keys": ([c_p, c_i64, c_p, c_p, c_p], c_i),
     "sixdgs_ls_partial_rows": ([], c_i),
     "sixdgs_score_pass2_batch_ls": ([c_p, c_i, c_i64, c_p, c_i, c_i, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_sz, c_p], c_i),

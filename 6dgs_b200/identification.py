@@ -12,12 +12,13 @@ a query is then two streaming passes over K (per-token softmax statistics, then 
 top-k and one fused pose-tail launch.  The [n_img, n_rays] attention map is only materialised when it
 is small (``attention_map_bytes_limit``); a 1M-Gaussian scene would need 30 GB.
 
-Training (SURVEY §8b "Autograd", §8f-3): the kernels have no backward.  When gradients are required
-(``torch.is_grad_enabled()`` and trainable hot-path parameters) ``run_attention`` / ``forward`` evaluate the
-same formulas with differentiable torch ops on the same CUDA device (``_run_attention_autograd``), so the
-reference's ``train_id_module`` keeps working; this is the training-mode implementation, not a fallback
-for a missing extension -- it refuses CPU tensors and still requires libsixdgs.so to be loadable.  The
-query path (``test_image`` / ``query_pose`` / ``ShardedPoseEstimator``) never takes it.
+Training (SURVEY §8b "Autograd", §8f-3): when gradients are required (``torch.is_grad_enabled()`` and trainable
+hot-path parameters) ``run_attention`` / ``forward`` take ``_run_attention_autograd``: the ray MLP and the two
+projections are differentiable torch ops (autograd owns their activations), while the softmax-over-rays score runs
+forward AND backward on the kernels (``_RayScoreFunction``: two streaming passes each way, no [n_img, n_rays] map saved),
+so the reference's ``train_id_module`` keeps working.  This is the training-mode implementation, not a fallback for a
+missing extension -- it refuses CPU tensors and requires libsixdgs.so.  The query path (``test_image`` /
+``query_pose`` / ``ShardedPoseEstimator``) never takes it.
 """
 from __future__ import annotations
 
@@ -98,6 +99,32 @@ class MultiHeadAttention(torch.nn.Module):
         m, z = ops.score_merge(pm, pz, q.shape[0])
         _, amap = ops.score_pass2(k, q, m, z, ops.SCORE_SIMT, want_map=True)
         return amap
+
+
+class _RayScoreFunction(torch.autograd.Function):
+    """scores = sum_i softmax_r(q k^T / sqrt(384)) with the forward AND the backward on the libsixdgs kernels (exact fp32
+    path): forward = the two streaming passes of the query path, backward = two more passes that form
+    dlogits = A (g - gbar) / sqrt(384) plus the GEMMs dk = dlogits q, dq = dlogits^T k (ops.score_backward).  The
+    [n_img, n_rays] attention map is returned (non-differentiable) only when asked -- the reference's training loop
+    reads nothing but its shape (train.py:159)."""
+
+    @staticmethod
+    def forward(ctx, q, k, want_map):
+        qd, kd = q.detach().float().contiguous(), k.detach().float().contiguous()
+        pm, pz = ops.score_pass1(kd, qd, ops.SCORE_SIMT)
+        m, z = ops.score_merge(pm, pz, qd.shape[0])
+        scores, amap = ops.score_pass2(kd, qd, m, z, ops.SCORE_SIMT, want_map=want_map)
+        ctx.save_for_backward(qd, kd, m, z)
+        if amap is None:
+            amap = torch.empty(qd.shape[0], 0, device=qd.device)
+        ctx.mark_non_differentiable(amap)
+        return scores, amap
+
+    @staticmethod
+    def backward(ctx, g, _g_map):
+        qd, kd, m, z = ctx.saved_tensors
+        dq, dk = ops.score_backward(kd, qd, m, z, g)
+        return dq, dk, None
 
 
 @dataclass
@@ -258,8 +285,15 @@ class IdentificationModule(torch.nn.Module):
         fea = rp.mlp2(torch.cat((rp.mlp(x), x), -1))
         q = lin(tok_pe, self.attention.q_proj.weight, self.attention.q_proj.bias)
         k = lin(fea, self.attention.k_proj.weight, self.attention.k_proj.bias)
-        amap = torch.softmax((q @ k.t()) / (q.shape[-1] ** 0.5), dim=-1)
-        return amap.sum(0), amap, tok, self._camera_up(grid)
+        if os.environ.get("SIXDGS_TRAIN_SCORE", "kernels") == "torch":  # pure torch-op route (kept as the cross-check)
+            amap = torch.softmax((q @ k.t()) / (q.shape[-1] ** 0.5), dim=-1)
+            return amap.sum(0), amap, tok, self._camera_up(grid)
+        # softmax-over-rays score: forward and backward on the kernels (no [n_img, n] map kept for the backward)
+        want_map = q.shape[0] * k.shape[0] * 4 <= self.attention_map_bytes_limit
+        scores, amap = _RayScoreFunction.apply(q, k, want_map)
+        if not want_map:
+            amap = torch.empty(q.shape[0], k.shape[0], device="meta")  # the shape is all train.py:159 reads
+        return scores, amap, tok, self._camera_up(grid)
 
     def forward(self, img, mask, rays_ori, rays_dir, rays_rgb, rays_to_test: int = -1):
         """Training-shaped variant (identification_module.py:94-115): random ray subset first."""

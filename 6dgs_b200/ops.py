@@ -392,6 +392,39 @@ def ls_solve(ls_sys: torch.Tensor, weight_scale: float = 1.0, up: Optional[torch
     return centre, watch, status
 
 
+def score_backward(k_f32: torch.Tensor, q: torch.Tensor, m: torch.Tensor, z: torch.Tensor, grad_scores: torch.Tensor,
+                   chunk: int = 1 << 18):
+    """Backward of scores = sum_i softmax_r(q k^T / sqrt(384)) w.r.t. q [n_img,384] and k [n,384] (fp32), given
+    dLoss/dscores [n] and the forward statistics (m, z): two streaming passes over the keys (csrc/score_simt.cu:
+    score_bwd_kernel) + two GEMMs per chunk of rays (sixdgs_linear).  -> (dq, dk)"""
+    k, q, g = f32c(k_f32), f32c(q), f32c(grad_scores)
+    n, n_img = k.shape[0], q.shape[0]
+    dev = k.device
+    parts = int(_lib.load().sixdgs_score_backward_parts())
+    part = torch.empty(parts, MAX_TOKENS, dtype=torch.float32, device=dev)
+    gbar = torch.empty(MAX_TOKENS, dtype=torch.float32, device=dev)
+    call("sixdgs_score_backward_gbar", dptr(k), n, dptr(q), n_img, dptr(m), dptr(z), dptr(g), dptr(part), dptr(gbar),
+         stream_ptr())
+    qt = torch.zeros(FEAT, MAX_TOKENS, dtype=torch.float32, device=dev)  # q^T, token axis padded to 256
+    qt[:, :n_img] = q.t()
+    dq = torch.zeros(MAX_TOKENS, FEAT, dtype=torch.float32, device=dev)
+    dk = torch.empty(n, FEAT, dtype=torch.float32, device=dev)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        c = hi - lo
+        ldt = -(-c // 16) * 16
+        dl = torch.empty(c, MAX_TOKENS, dtype=torch.float32, device=dev)
+        dlt = torch.zeros(MAX_TOKENS, ldt, dtype=torch.float32, device=dev)
+        call("sixdgs_score_backward_dlogits", dptr(k[lo:hi]), c, dptr(q), n_img, dptr(m), dptr(z), dptr(g[lo:hi]), dptr(gbar),
+             dptr(dl), dptr(dlt), ldt, stream_ptr())
+        call("sixdgs_linear", dptr(dl), c, MAX_TOKENS, MAX_TOKENS, dptr(qt), None, FEAT, dptr(dk[lo:hi]), FEAT, 0,
+             stream_ptr())                                     # dk = dlogits q
+        kt = torch.zeros(FEAT, ldt, dtype=torch.float32, device=dev)
+        kt[:, :c] = k[lo:hi].t()
+        dq += linear(dlt, kt, None)                            # dq += dlogits^T k
+    return dq[:n_img].contiguous(), dk
+
+
 def topk(scores: torch.Tensor, k: int):
     n = scores.shape[0]
     vals = torch.empty(k, dtype=torch.float32, device=scores.device)

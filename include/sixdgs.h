@@ -158,6 +158,19 @@ int sixdgs_score_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const f
                        const float* m, const float* z, float* scores, float* attn_map, int impl,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a11 backward (training: autograd through our_multihead_attention.py:4-12 + identification_module.py:80-82,
+ * driven by pose_estimation/train.py:146-176).  fp32 keys.  With g = dLoss/dscores [n_rays] and the forward's (m, z):
+ *   gbar[t]       = sum_r A[t,r] g[r]                                   (part_gbar: sixdgs_score_backward_parts() x 256 scratch)
+ *   dlogits[r,t]  = A[t,r] (g[r] - gbar[t]) / sqrt(384)                 row-major [n_rays,256]; dlogits_t (nullable) the
+ *                   same values transposed, [256, ldt] with ldt >= n_rays
+ * The parameter gradients are then two GEMMs (sixdgs_linear): dk = dlogits q, dq = dlogits^T k. */
+int sixdgs_score_backward_parts(void);
+int sixdgs_score_backward_gbar(const float* k_f32, int64_t n_rays, const float* q, int n_img, const float* m,
+                               const float* z, const float* grad_scores, float* part_gbar, float* gbar, void* stream);
+int sixdgs_score_backward_dlogits(const float* k_f32, int64_t n_rays, const float* q, int n_img, const float* m,
+                                  const float* z, const float* grad_scores, const float* gbar, float* dlogits,
+                                  float* dlogits_t, int64_t ldt, void* stream);
+
 /* fp32 keys [n,384] -> SIXDGS_F16X2 rows [n,768]; absmax (nullable, device, zero-initialised by the caller) receives
  * max |16 k| over the converted rows so the caller can check the fp16 range (must stay < 65504). */
 int sixdgs_split_keys(const float* k_f32, int64_t n, void* k_out, float* absmax, void* stream);

@@ -304,3 +304,58 @@ def test_offline_eval_driver_end_to_end(sx, synthetic, tmp_path):
     assert torch.isfinite(pred).all()
     rot = pred[:, :3, :3]
     torch.testing.assert_close(rot @ rot.transpose(1, 2), torch.eye(3).expand(3, 3, 3), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,n_img,q_scale", [(1, 256, 1.0), (1000, 201, 1.0), (3017, 256, 8.0), (70_003, 256, 3.0)])
+def test_score_backward_kernels_vs_fp64_autograd(sx, n, n_img, q_scale):
+    """d(sum_i softmax_r(q k^T / sqrt(384))) / d(q, k) from the backward kernels (two streaming passes + two GEMMs)
+    against torch autograd in fp64 (what train.py:176 `loss.backward()` computes through the reference's attention)"""
+    from importlib import import_module
+    fn = import_module("6dgs_b200.identification")._RayScoreFunction
+    dev = "cuda"
+    gen = torch.Generator().manual_seed(n)
+    q = (torch.randn(n_img, 384, generator=gen) * q_scale).to(dev).requires_grad_(True)
+    k = (torch.randn(n, 384, generator=gen) * 0.7).to(dev).requires_grad_(True)
+    g = torch.randn(n, generator=gen).to(dev)
+    scores, amap = fn.apply(q, k, n <= 3017)
+    (scores * g).sum().backward()
+    q64, k64 = q.detach().double().requires_grad_(True), k.detach().double().requires_grad_(True)
+    a64 = torch.softmax((q64 @ k64.t()) / 384 ** 0.5, dim=-1)
+    (a64.sum(0) * g.double()).sum().backward()
+    torch.testing.assert_close(scores.detach().double(), a64.sum(0).detach(), rtol=1e-3, atol=0)
+    if n <= 3017:
+        torch.testing.assert_close(amap.double(), a64.detach(), rtol=1e-3, atol=1e-12)
+    for mine, ref, name in ((q.grad, q64.grad, "dq"), (k.grad, k64.grad, "dk")):
+        err = (mine.double() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+        assert err < 2e-4, (name, err)
+
+
+def test_training_step_gradients_kernels_vs_torch_route(sx, synthetic, monkeypatch):
+    """forward() under autograd (train_id_module's call, train.py:146-176): parameter gradients with the score
+    forward/backward on the kernels equal those of the pure torch-op route"""
+    from conftest import load_golden
+    dev = "cuda"
+    r, g = load_golden("rays_small.npz"), load_golden("id_module.npz")
+    ori, dirs, rgb = r["ori"][:3000].to(dev), r["dirs"][:3000].to(dev), r["rgb"][:3000].to(dev)
+    img, mask = g["img"].to(dev), torch.ones(64, 64, dtype=torch.bool, device=dev)
+    target = torch.rand(2500, generator=torch.Generator().manual_seed(1)).to(dev) * 0.1
+    grads = {}
+    for route in ("kernels", "torch"):
+        monkeypatch.setenv("SIXDGS_TRAIN_SCORE", route)
+        idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone(), score_impl="simt_fp32")
+        idm.load_state_dict(synthetic.synth_id_weights(seed=3, q_gain=8.0), strict=False)
+        idm = idm.to(dev).train()
+        torch.manual_seed(0)
+        scores, amap, tok, up, used = idm(img, mask, ori, dirs, rgb, rays_to_test=2500)
+        assert amap.shape == (256, 2500)
+        loss = torch.square(scores - target).mean() + 0.1 * (0.5 - 0.5 * up[2])  # train.py:161-170 shape of the loss
+        loss.backward()
+        grads[route] = {n_: p.grad.clone() for n_, p in idm.named_parameters()
+                        if p.grad is not None and n_.startswith(("ray_preprocessor", "attention"))}
+    assert set(grads["kernels"]) == set(grads["torch"]) and len(grads["torch"]) == 12
+    # (the softmax over rays is invariant to a constant added to every key, so the gradients of mlp2.2.bias and
+    # k_proj.bias are exactly zero in exact arithmetic -- rounding noise in both routes: absolute floor below)
+    floor = 1e-5 * max(gt.abs().max().item() for gt in grads["torch"].values())
+    for n_, gt in grads["torch"].items():
+        gk = grads["kernels"][n_]
+        assert (gk - gt).abs().max().item() <= 2e-3 * gt.abs().max().item() + floor, n_
