@@ -78,6 +78,9 @@ def parse():
     ap.add_argument("--config", choices=("c3", "c5"), default="c3",
                     help="c3 = BASELINE configs[2]/[3] (1M Gaussians, 8 queries per step); c5 = configs[4] (5M Gaussians, "
                          "32 queries per step, 8 GPUs); explicit --gaussians / --batch override")
+    ap.add_argument("--emulate-shard", type=int, default=0, metavar="W",
+                    help="single process, but generate and score only rank 0's share of a W-rank run (ray shard 0 of W, one "
+                         "image of the batch per W): the per-rank kernel list of an N = W run for ncu, which cannot wrap torchrun")
     ap.add_argument("--no-latency", action="store_true", help="skip the one-query-per-step figure (profiling runs)")
     ap.add_argument("--no-breakdown", action="store_true", help="skip the eager per-stage CUDA-event breakdown")
     ap.add_argument("--batch", type=int, default=None,
@@ -442,7 +445,8 @@ def main():
     scene = sx.GaussianScene.from_dict(sc, device=dev)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    ori, dirs, rgb = sx.generate_all_possible_rays(scene, max_ellipsoids=None, shard=(rank, world) if world > 1 else None)
+    shard = (rank, world) if world > 1 else ((0, args.emulate_shard) if args.emulate_shard > 1 else None)
+    ori, dirs, rgb = sx.generate_all_possible_rays(scene, max_ellipsoids=None, shard=shard)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     import warnings
@@ -617,7 +621,17 @@ def main():
                 est2.query_batch(img_dev, mask_dev)
             f1.record()
             torch.cuda.synchronize()
+            # the HBM-bound formulation (one query per sweep over 768-B keys, score_tc.cu): the "ray-score HBM GB/s" figure
+            h1, h2 = time_score_kernels(sx, idm2, cache2, dev, 1, 4, 1, False)
+            hb = {}
+            for nm, ts, by in (("pass1", h1, n_local * 768 + 74 * 2 * 256 * 4), ("pass2", h2, n_local * 772)):
+                ms_ = sum(ts) / len(ts)
+                hb[nm] = {"ms": ms_, "GBps": by / ms_ / 1e6, "hbm_frac": by / ms_ / 1e6 / peaks["hbm_gbs"],
+                          "TFLOPs": 2.0 * 256 * 384 * n_local / ms_ / 1e9}
             secondary = {"score_impl": "tc_bf16", "value": B * n2 / (f0.elapsed_time(f1) / 1e3), "unit": "queries/s", "steps": n2,
+                         "hbm_bound_kernel": {"kernel": "score_tc_kernel<1|2> (bf16 keys, one query per sweep)", "sustained": hb,
+                                              "note": "256 MMA-FLOP per key byte = on the ridge: this is the formulation whose roof is "
+                                                      "HBM; measured right after the throughput-mode steps (power-capped state)"},
                          "note": "throughput mode (one bf16 MMA term, 768 B/ray, TF32 key build): 3e-2 score tolerance on flat "
                                  "logits, NOT parity-green on a peaked softmax (tests/test_gpu_exact_tc.py) -- reported for "
                                  "reference only, the headline is the exact mode"}
