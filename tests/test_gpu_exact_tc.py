@@ -297,3 +297,39 @@ def test_exact_tensor_core_key_build_vs_fp64(sx, synthetic, n):
     c2 = idm.build_key_cache(ori, dirs, rgb)
     r2 = (c2.keys[:, :384].double() + c2.keys[:, 384:].double()) / 16.0
     assert (r2 - rec).abs().max().item() / scale < 5e-6
+
+
+def test_f16x2_edge_cases(sx, synthetic):
+    """tiny ray sets, a single token, an empty ray set, and keys outside the fp16 range of the exact format"""
+    idm = make_module(sx, synthetic, "tc_f16x2")
+    gen = torch.Generator().manual_seed(5)
+    for n, n_img in ((1, 1), (3, 256), (127, 5), (129, 256)):
+        k = (torch.randn(n, 384, generator=gen) * 0.7).to(DEV)
+        q = (torch.randn(n_img, 384, generator=gen) * 4.0).to(DEV)
+        keys = sx.ops.split_keys(k)
+        pm, pz = sx.ops.score_pass1(keys, q, sx.ops.SCORE_TC)
+        m, z = sx.ops.score_merge(pm, pz, n_img)
+        s, _ = sx.ops.score_pass2(keys, q, m, z, sx.ops.SCORE_TC)
+        ref, _ = fp64_scores(q, k)
+        assert rel_err(s, ref) < 1e-3 and abs(s.double().sum().item() - n_img) < 1e-3 * n_img
+    # no rays: an empty cache builds, scoring it is refused with a clear error (the C ABI needs n_rays >= 1)
+    z3 = torch.zeros(0, 3, device=DEV)
+    cache = idm.build_key_cache(z3, z3, z3)
+    assert cache.keys.shape == (0, 768) and cache.n_rays == 0
+    with pytest.raises(sx.SixdgsError):
+        sx.ops.score_pass1(cache.keys, torch.randn(256, 384, device=DEV), sx.ops.SCORE_TC)
+    # |16 k| beyond the fp16 range: split_keys reports it, the module's builder refuses the cache
+    big = torch.full((4, 384), 5000.0, device=DEV)
+    absmax = torch.zeros(1, device=DEV)
+    sx.ops.split_keys(big, absmax=absmax)
+    assert absmax.item() >= 65504.0
+    import copy
+    idm2 = copy.deepcopy(idm)
+    with torch.no_grad():
+        idm2.attention.k_proj.bias.fill_(5000.0)
+    o = torch.randn(10, 3, device=DEV)
+    with pytest.raises(sx.SixdgsError, match="fp16 range"):
+        idm2.build_key_cache(o, torch.nn.functional.normalize(o, dim=-1), torch.rand(10, 3, device=DEV))
+    # a wrongly shaped cache is rejected before any launch
+    with pytest.raises(sx.SixdgsError):
+        sx.ops.score_pass1(torch.zeros(8, 384, dtype=torch.float16, device=DEV), torch.randn(256, 384, device=DEV), sx.ops.SCORE_TC)
