@@ -34,8 +34,9 @@ _SIGNATURES = {
     "sixdgs_knn_grid_workspace": ([c_i64, c_i64], c_sz),
     "sixdgs_knn_normals_grid": ([c_p, c_i64, c_i64, c_i64, c_i, c_p, ctypes.c_float, c_p, c_p, c_p, c_sz, c_p], c_i),
     "sixdgs_sym_eig3x3": ([c_p, c_i64, ctypes.c_float, c_p, c_p, c_p], c_i),
-    "sixdgs_raygen_count": ([c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_i, c_i, c_p, c_p, c_p], c_i),
-    "sixdgs_raygen_fill": ([c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_i64, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p], c_i),
+    "sixdgs_raygen_cells": ([c_p, c_p, c_i64, c_i, c_p, c_p], c_i),
+    "sixdgs_raygen_fill": ([c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_i64, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p], c_i),
+    "sixdgs_raygen_compact": ([c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p], c_i),
     "sixdgs_exclusive_scan": ([c_p, c_i64, c_p, c_p], c_i),
     "sixdgs_ray_features_workspace": ([c_i64], c_sz),
     "sixdgs_ray_features": ([c_p, c_p, c_p, c_i64] + [c_p] * 10 + [c_p, c_i, c_p, c_i, c_p, c_sz, c_p], c_i),

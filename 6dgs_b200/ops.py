@@ -96,33 +96,42 @@ def exclusive_scan(counts: torch.Tensor) -> torch.Tensor:
 
 def raygen(xyz, scaling_raw, rotation_raw, features, sh_degree: int, sel: torch.Tensor, normals: Optional[torch.Tensor],
            target_points: int = 50, resolution: int = 1000, mode: int = 0):
-    """Two launches (count, fill) with one device->host read of the total ray count in between --
-    the same single sync the reference has at sampling.py:145."""
+    """cells per ellipsoid (cheap) -> scan -> ONE table pass that writes each ellipsoid's rays densely at its cell
+    offset -> scan of the surviving counts -> block copy to the gap-free arrays.  Two small device->host reads (total
+    cells, total rays); the reference has the same kind of sync at sampling.py:145."""
     dev = scaling_raw.device
     m = sel.shape[0]
-    rays_per = torch.empty(m, dtype=torch.int32, device=dev)
-    cells_per = torch.empty(m, dtype=torch.int32, device=dev)
     s = stream_ptr()
-    call("sixdgs_raygen_count", dptr(xyz), dptr(scaling_raw), dptr(rotation_raw), dptr(sel, torch.int64), m,
-         dptr(normals), target_points, resolution, mode, dptr(rays_per, torch.int32), dptr(cells_per, torch.int32), s)
+    cells_per = torch.empty(m, dtype=torch.int32, device=dev)
+    call("sixdgs_raygen_cells", dptr(scaling_raw), dptr(sel, torch.int64), m, target_points, dptr(cells_per, torch.int32), s)
+    slot = exclusive_scan(cells_per)
+    n_slots = int(slot[-1].item())
+    rays_per = torch.zeros(m, dtype=torch.int32, device=dev)
+    full = mode == 0
+    t_ori = torch.empty(max(n_slots, 1), 3, dtype=torch.float32, device=dev)
+    t_dir = torch.empty(max(n_slots, 1), 3, dtype=torch.float32, device=dev) if full else None
+    t_rgb = torch.empty(max(n_slots, 1), 3, dtype=torch.float32, device=dev) if full else None
+    t_ell = torch.empty(max(n_slots, 1), dtype=torch.int64, device=dev)
+    sh_coeffs = 16
+    if features is not None:
+        if features.dim() != 3 or features.shape[2] != 3 or features.shape[1] < (sh_degree + 1) ** 2:
+            raise _lib.SixdgsError(f"features must be [N, >= (sh_degree+1)^2, 3] (get_features layout); got "
+                                   f"{tuple(features.shape)} for sh_degree {sh_degree}")
+        sh_coeffs = int(features.shape[1])
+    if n_slots:
+        call("sixdgs_raygen_fill", dptr(xyz), dptr(scaling_raw), dptr(rotation_raw), dptr(features), sh_degree, sh_coeffs,
+             dptr(sel, torch.int64), m, dptr(normals), target_points, resolution, mode, dptr(slot, torch.int64),
+             dptr(t_ori), dptr(t_dir), dptr(t_rgb), dptr(t_ell, torch.int64), dptr(rays_per, torch.int32), s)
     offs = exclusive_scan(rays_per)
     n_rays = int(offs[-1].item())
     ori = torch.empty(n_rays, 3, dtype=torch.float32, device=dev)
     ell = torch.empty(n_rays, dtype=torch.int64, device=dev)
-    dirs = rgb = None
-    if mode == 0:
-        dirs = torch.empty(n_rays, 3, dtype=torch.float32, device=dev)
-        rgb = torch.empty(n_rays, 3, dtype=torch.float32, device=dev)
+    dirs = torch.empty(n_rays, 3, dtype=torch.float32, device=dev) if full else None
+    rgb = torch.empty(n_rays, 3, dtype=torch.float32, device=dev) if full else None
     if n_rays:
-        sh_coeffs = 16
-        if features is not None:
-            if features.dim() != 3 or features.shape[2] != 3 or features.shape[1] < (sh_degree + 1) ** 2:
-                raise _lib.SixdgsError(f"features must be [N, >= (sh_degree+1)^2, 3] (get_features layout); got "
-                                       f"{tuple(features.shape)} for sh_degree {sh_degree}")
-            sh_coeffs = int(features.shape[1])
-        call("sixdgs_raygen_fill", dptr(xyz), dptr(scaling_raw), dptr(rotation_raw), dptr(features), sh_degree, sh_coeffs,
-             dptr(sel, torch.int64), m, dptr(normals), target_points, resolution, mode, dptr(offs, torch.int64),
-             dptr(ori), dptr(dirs), dptr(rgb), dptr(ell, torch.int64), s)
+        call("sixdgs_raygen_compact", dptr(slot, torch.int64), dptr(offs, torch.int64), dptr(rays_per, torch.int32), m,
+             dptr(t_ori), dptr(t_dir), dptr(t_rgb), dptr(t_ell, torch.int64), dptr(ori), dptr(dirs), dptr(rgb),
+             dptr(ell, torch.int64), s)
     return ori, dirs, rgb, ell, cells_per
 
 

@@ -139,6 +139,9 @@ class ShardedPoseEstimator:
         if self.multi_query:  # per query only the merge remains; per batch (of <= 8) q-prep + kernel for each pass
             self.launches_per_query -= 2 + tc
             self.launches_per_batch += 4
+        if self.solve == "weighted_ls":  # no top-k / candidate exchange / pose tail: merge per query; per batch the
+            self.launches_per_query = 1  # partial-system reduction and one solve for all queries
+            self.launches_per_batch += 2
         self._g = None  # captured graphs + static buffers
 
     # ------------------------------------------------------------------ collectives

@@ -78,21 +78,26 @@ int sixdgs_sym_eig3x3(const float* A, int64_t n, float eps, float* vals, float* 
 /* ---- a6+a7+a8: candidate-ray generation -------- quadricell.py:191-386, sampling.py:116-124,176-251,
  *                                                  utils/sh_utils.py:55-118, general_utils.py:103-126
  * sel[m] = global Gaussian ids of the selected (valid, permuted) ellipsoids; normals[m,3] from a4.
- * Count mode: rays_per_ell[m] and cells_per_ell[m] (nullable) are written.
- * Fill mode:  ray_offset[m] = exclusive scan of rays_per_ell; writes ori/dir/rgb[n_rays,3] and
- *             ell_id[n_rays] (local index into sel; nullable) in ellipsoid-, ring-, cell-major order.
+ * Every ring's arc-length table is built once:
+ *   1. sixdgs_raygen_cells:   cells_per_ell[m] (ring layout only; an upper bound of the ellipsoid's rays)
+ *   2. sixdgs_exclusive_scan: slot_offset[m+1]; the caller sizes scratch arrays for slot_offset[m] rays
+ *   3. sixdgs_raygen_fill:    writes each ellipsoid's surviving rays densely from slot_offset[e] into the scratch
+ *                             ori/dir/rgb[., 3] and ell_id[.] (local index into sel; nullable) in ring-, cell-major
+ *                             order, and rays_per_ell[m]
+ *   4. sixdgs_exclusive_scan: ray_offset[m+1]  ->  5. sixdgs_raygen_compact: the gap-free final arrays.
  * mode 0 = rays (rotate, hemisphere quirk n_x*p'_x > 0, normalise, +mu, SH colour);
  * mode 1 = raw quadricell cells (a6 only: un-rotated points -> ori, no mask; dir/rgb untouched). */
-int sixdgs_raygen_count(const float* xyz, const float* scaling_raw, const float* rotation_raw,
-                        const int64_t* sel, int64_t m, const float* normals, int target_points,
-                        int resolution, int mode, int32_t* rays_per_ell, int32_t* cells_per_ell,
-                        void* stream);
+int sixdgs_raygen_cells(const float* scaling_raw, const int64_t* sel, int64_t m, int target_points,
+                        int32_t* cells_per_ell, void* stream);
 int sixdgs_raygen_fill(const float* xyz, const float* scaling_raw, const float* rotation_raw,
                        const float* features /* [N,sh_coeffs,3] = get_features */, int sh_degree,
                        int sh_coeffs /* stored coefficients per Gaussian, >= (sh_degree+1)^2; 16 for degree-3 storage */,
                        const int64_t* sel, int64_t m, const float* normals, int target_points,
-                       int resolution, int mode, const int64_t* ray_offset, float* ori, float* dir,
-                       float* rgb, int64_t* ell_id, void* stream);
+                       int resolution, int mode, const int64_t* slot_offset, float* ori, float* dir,
+                       float* rgb, int64_t* ell_id, int32_t* rays_per_ell, void* stream);
+int sixdgs_raygen_compact(const int64_t* slot_offset, const int64_t* ray_offset, const int32_t* rays_per_ell, int64_t m,
+                          const float* tmp_ori, const float* tmp_dir, const float* tmp_rgb, const int64_t* tmp_ell,
+                          float* ori, float* dir, float* rgb, int64_t* ell_id, void* stream);
 /* exclusive scan int32 -> int64 with the total in out[n] (out has n+1 entries).  Single block. */
 int sixdgs_exclusive_scan(const int32_t* in, int64_t n, int64_t* out, void* stream);
 
