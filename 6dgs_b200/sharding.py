@@ -381,6 +381,9 @@ class ShardedPoseEstimator:
                         g["out"] = self._stage3(g["allc"], g["st"]["up"], k, g["st"]["nb"])
                 g["graphs"] = [g1, g2, g3]
             torch.cuda.synchronize()
+            # buffers that were allocated by the warm-up calls (outside the capture) but are baked into the graphs:
+            # keep them alive with the graphs, or a later eager call with a larger batch would free them under a replay
+            g["keepalive"] = (self._scores_b, self.cache.scores, self.cache.keys, self.ori, self.dirs)
             self._g = g
             return True
         except Exception as e:  # noqa: BLE001
