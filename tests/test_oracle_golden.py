@@ -110,3 +110,49 @@ def test_line_intersection(oracle):
     assert torch.isnan(g["c_parallel"]).all()
     assert torch.equal(oracle.exclude_negatives(c, g["o"], g["d"]), g["neg_mask"])
     torch.testing.assert_close(oracle.make_rotation_mat(g["rot_dir"], g["rot_up"]), g["rot"], rtol=1e-6, atol=1e-7)
+
+
+def test_peaked_softmax_fixture(oracle, synthetic, sx):
+    """The oracle against the reference on the PEAKED fixture (attention.q_proj x20: logit std 6.5): scores, row
+    statistics, top-100 and the full pose of test_pose_estimation.  Also the arithmetic that decides the score format of
+    the GPU path: the same logits with bf16 / fp16 operand rounding (what a single tensor-core term computes) miss the
+    north_star bar, the fp16 hi+lo three-term form does not."""
+    g = load_golden("id_module_peaked.npz")
+    r = load_golden("rays_small.npz")
+    i = load_golden("id_module.npz")
+    w = synthetic.synth_id_weights(seed=g["weight_seed"], q_gain=float(g["q_gain"]))
+    fea = oracle.ray_features(r["ori"], r["dirs"], r["rgb"], w)
+    score, _ = oracle.attention_scores(i["tok_pe"], fea, w, return_map=False)
+    torch.testing.assert_close(score, g["scores"], rtol=2e-4, atol=0)
+    top = torch.topk(score, 100)
+    assert set(top.indices.tolist()) == set(g["topk_idx"].tolist())
+    # the pose of the fixture comes from test_pose_estimation on the uint8 image (test.py:69-73 divides by 255): same
+    # route here -- torch front end (boundary components, CPU) -> oracle scores -> oracle pose tail
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone())
+    idm.load_state_dict(w, strict=False)
+    with torch.no_grad():
+        tok_pe, _, grid = idm.backbone_wrapper(g["img_u8"].float() / 255.0, torch.ones(64, 64, dtype=torch.bool))
+        up = idm._camera_up(grid)
+    s8, _ = oracle.attention_scores(tok_pe, fea, w, return_map=False)
+    t8 = torch.topk(s8, 100)
+    c2w, _ = oracle.pose_tail(t8.indices, t8.values, r["ori"], r["dirs"], up)
+    torch.testing.assert_close(c2w, g["pred_c2w"], rtol=1e-4, atol=1e-4)
+    # operand-rounding study in fp64 (exact products and sums, only the operands are rounded)
+    q = torch.nn.functional.linear(i["tok_pe"], w["attention.q_proj.weight"], w["attention.q_proj.bias"]).double()
+    k = torch.nn.functional.linear(fea, w["attention.k_proj.weight"], w["attention.k_proj.bias"]).double()
+    ref = torch.softmax(q @ k.t() / 384 ** 0.5, -1).sum(0)
+
+    def err(logits):
+        s = torch.softmax(logits / 384 ** 0.5, -1).sum(0)
+        return ((s - ref).abs() / ref).max().item()
+
+    def split(x, dt):
+        hi = x.float().to(dt).double()
+        return hi, (x - hi).float().to(dt).double()
+
+    e_bf16 = err(q.float().to(torch.bfloat16).double() @ k.float().to(torch.bfloat16).double().t())
+    e_fp16 = err(q.float().half().double() @ k.float().half().double().t())
+    qh, ql = split(q, torch.float16)
+    kh, kl = split(k, torch.float16)
+    e_x2 = err(qh @ kh.t() + qh @ kl.t() + ql @ kh.t())
+    assert e_bf16 > 1e-2 and e_fp16 > 2e-3 and e_x2 < 1e-5, (e_bf16, e_fp16, e_x2)
