@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsixdgs.so")
-F32, BF16, F16X2 = 0, 1, 2
+F32, BF16, F16X2, F16F8 = 0, 1, 2, 3
 FEAT = 384
 MAX_TOKENS = 256
 
@@ -57,6 +57,7 @@ _SIGNATURES = {
     "sixdgs_score_backward_gbar": ([c_p, c_i64, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p], c_i),
     "sixdgs_score_backward_dlogits": ([c_p, c_i64, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p], c_i),
     "sixdgs_split_keys": ([c_p, c_i64, c_p, c_p, c_p], c_i),
+    "sixdgs_keys_f16x2_to_f16f8": ([c_p, c_i64, c_p], c_i),
     "sixdgs_ls_partial_rows": ([], c_i),
     "sixdgs_score_pass2_batch_ls": ([c_p, c_i, c_i64, c_p, c_i, c_i, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_sz, c_p], c_i),
     "sixdgs_ls_solve": ([c_p, c_i, ctypes.c_double, c_p, c_p, c_p, c_p, c_p, c_p, c_p], c_i),

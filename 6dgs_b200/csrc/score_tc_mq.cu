@@ -1,6 +1,9 @@
 // a11, several queries per key sweep (SURVEY §8d "ray-score, batch" row), in two key formats:
-//   bf16   (SPLIT = false): one MMA term, 768 B/ray -- the throughput mode (3e-2 score tolerance);
-//   f16x2  (SPLIT = true):  every key and every query element is carried as an fp16 pair hi + lo (22 significant
+//   bf16   (FMT 0): one MMA term, 768 B/ray -- the throughput mode (3e-2 score tolerance);
+//   f16f8  (FMT 2): the main term Qh.Kh in fp16 and the two 2^-11 cross terms in e4m3 at twice the tensor rate (two
+//          term-units instead of three); the cross terms are then good to ~5 %, i.e. the logits to ~0.05 x the fp16
+//          rounding error: inside the 1e-3 bar for logit standard deviations up to ~12, without the margin of f16x2;
+//   f16x2  (FMT 1): every key and every query element is carried as an fp16 pair hi + lo (22 significant
 //          bits) and the logit is the three-term product  Qh.Kh + Qh.Kl + Ql.Kh  accumulated in one fp32 TMEM
 //          accumulator (the dropped Ql.Kl term is 2^-22 relative) -- the EXACT tensor-core mode: scores agree with the
 //          fp32 reference to ~1e-5 even for a peaked (trained) softmax where bf16 logits are off by 1e-1.
@@ -36,6 +39,7 @@
 // (weights = score / n_img) -- per-CTA fp64 partial sums of R (6), q (3), sum w d (3), sum w (1) from the scores the
 // epilogue already holds (+24 B/ray for origin and direction), reduced by sixdgs_ls_reduce / one 13-double allreduce.
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "tc_common.cuh"
 
 namespace sixdgs {
@@ -53,24 +57,32 @@ constexpr float kMqLog2e = 1.4426950408889634f;
 constexpr float kMqLn2 = 0.6931471805599453f;
 constexpr float kMqQScale = 1.4426950408889634f / 19.595917942265423f;  // log2(e) / sqrt(384)
 
-template <bool SPLIT>
+constexpr int kFmtBf16 = 0, kFmtF16x2 = 1, kFmtF16F8 = 2;
+template <int FMT>
 struct MqCfg {
-  static constexpr int kStages = SPLIT ? 7 : 6;
-  static constexpr int kRow = SPLIT ? 2 * kFeat : kFeat;          // elements per cache / query row
-  static constexpr uint32_t kIdesc = umma_idesc(SPLIT ? 0u : 1u, 256, 256);  // fp16 or bf16 -> fp32, M = N = 256
+  static constexpr int kStages = FMT == kFmtF16x2 ? 7 : (FMT == kFmtF16F8 ? 4 : 6);
+  static constexpr int kResident = FMT == kFmtF16F8 ? 9 : 6;   // resident 16 KB key boxes per CTA (f16f8: 6 x Kh + 3 x Kh8)
+  static constexpr int kRowBytes = FMT == kFmtBf16 ? 768 : 1536;   // bytes per cache / query row
+  // bf16 (1) or fp16 (0) -> fp32, M = N = 256; kind::f8f6f4 uses the same field with E4M3 = 0
+  static constexpr uint32_t kIdesc = umma_idesc(FMT == kFmtBf16 ? 1u : 0u, 256, 256);
 };
 constexpr float kMqKeyScale = 16.0f;                 // f16x2: stored key = 16 k
 constexpr float kMqQryScale = 64.0f;                 // f16x2: stored query = 64 log2(e)/sqrt(384) q
 constexpr float kMqSplitOut = 1.0f / 1024.0f;        // accumulator -> log2-domain logit
+// f16f8 row: [hi fp16 (768 B) | hi8 e4m3 (384 B) | lo8 e4m3 (384 B)].  The e4m3 copies carry power-of-two scales chosen so that
+// the cross products land on the scale of the main term (one shared accumulator) and inside e4m3's normal range:
+//   keys:    hi8 = e4m3(hi / 64)  (= k / 4),            lo8 = e4m3(64 lo)
+//   queries: hi8 = e4m3(hi / 64)  (= log2e/sqrt(384) q), lo8 = e4m3(64 lo)        -> Qh8.Kl8 = Qh.Kl,  Ql8.Kh8 = Ql.Kh
+constexpr float kMqF8Down = 1.0f / 64.0f, kMqF8Up = 64.0f;
 
 // (no struct-level alignment attribute: the kernel aligns the base to 1024 B by hand and sizeof must not be padded --
 // the f16x2 variant uses all but 768 B of the 227 KB a CTA can have)
-template <int STAGES>
+template <int STAGES, int RES>
 struct MqSmem {
-  uint8_t kt[kMqKBlocks][kMqKBBytes];  //  96 KB: this CTA's 128 rays of the current tile (f16x2: the hi halves)
-  uint8_t qs[STAGES][kMqKBBytes];      //  96 / 112 KB: token ring (f16x2: query hi, key lo, query lo blocks)
-  uint64_t k_full[kMqKBlocks];
-  uint64_t k_empty[kMqKBlocks];
+  uint8_t kt[RES][kMqKBBytes];         //  96 / 144 KB: this CTA's 128 rays of the current tile (hi halves; f16f8: + e4m3 copy)
+  uint8_t qs[STAGES][kMqKBBytes];      //  96 / 112 / 64 KB: token ring (f16x2: query hi, key lo, query lo blocks)
+  uint64_t k_full[RES];
+  uint64_t k_empty[RES];
   uint64_t q_full[STAGES];
   uint64_t q_empty[STAGES];
   uint64_t tmem_full[2];
@@ -86,13 +98,22 @@ struct MqSmem {
   };
   float xch[2][128];                   // column-half exchange (pass 1's final merge borrows ring stage 0 for a second one)
 };
-static_assert(sizeof(MqSmem<7>) + 1024 <= 232448, "f16x2 variant exceeds the 227 KB shared-memory limit");
+static_assert(sizeof(MqSmem<7, 6>) + 1024 <= 232448, "f16x2 variant exceeds the 227 KB shared-memory limit");
+static_assert(sizeof(MqSmem<4, 9>) + 1024 <= 232448, "f16f8 variant exceeds the 227 KB shared-memory limit");
 
 __device__ __forceinline__ void mq_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mq_umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -179,7 +200,44 @@ __global__ void mq_split_keys_kernel(const float* __restrict__ k, int64_t n, __h
   }
 }
 
-template <int PASS, bool SPLIT>
+__device__ __forceinline__ uint8_t mq_e4m3(float x) {
+  return (uint8_t)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3);
+}
+// f16f8 query rows: [hi fp16 | e4m3(hi / 64) | e4m3(64 lo)] of 64 * log2(e)/sqrt(384) * q
+__global__ void mq_qprep_f8_kernel(const float* __restrict__ q, int n_img, int nq, uint8_t* __restrict__ qb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)nq * kMaxTokens * kFeat) return;
+  const int64_t row = i / kFeat;
+  const int col = (int)(i % kFeat);
+  const int t = (int)(row % kMaxTokens);
+  const float x = t < n_img ? q[i] * (kMqQScale * kMqQryScale) : 0.0f;
+  const __half hi = __float2half_rn(x);
+  const float hf = __half2float(hi);
+  uint8_t* r = qb + row * 1536;
+  reinterpret_cast<__half*>(r)[col] = hi;
+  r[768 + col] = mq_e4m3(hf * kMqF8Down);
+  r[1152 + col] = mq_e4m3((x - hf) * kMqF8Up);
+}
+// f16x2 key rows [hi | lo] (fp16) -> f16f8 rows [hi | e4m3(hi / 64) | e4m3(64 lo)], IN PLACE (same 1536 B): one warp
+// per row reads the whole row into registers before it overwrites the lo half
+__global__ void __launch_bounds__(256) mq_keys_to_f8_kernel(uint8_t* __restrict__ keys, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  uint8_t* r = keys + row * 1536;
+  const __half* h = reinterpret_cast<const __half*>(r);
+  float hi[12], lo[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) { hi[j] = __half2float(h[lane + 32 * j]); lo[j] = __half2float(h[kFeat + lane + 32 * j]); }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    r[768 + lane + 32 * j] = mq_e4m3(hi[j] * kMqF8Down);
+    r[1152 + lane + 32 * j] = mq_e4m3(lo[j] * kMqF8Up);
+  }
+}
+
+template <int PASS, int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMqThreads, 1)
 score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_q,
                    int64_t n_rays, int n_img, int nq,
@@ -188,11 +246,15 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
                    float* __restrict__ scores, int64_t score_stride,            // pass 2 out [nq, score_stride]
                    const float* __restrict__ rays_ori, const float* __restrict__ rays_dir,  // pass 2, fused LS (nullable)
                    double* __restrict__ ls_part) {                              // pass 2 out [nq, 2*pairs, 13]
-  using Cfg = MqCfg<SPLIT>;
+  using Cfg = MqCfg<FMT>;
+  constexpr bool SPLIT = FMT == kFmtF16x2;
+  constexpr bool F8 = FMT == kFmtF16F8;
   constexpr int kStages = Cfg::kStages;
-  constexpr float kSc = SPLIT ? kMqSplitOut : 1.0f;
+  constexpr int kRes = Cfg::kResident;
+  constexpr float kSc = FMT == kFmtBf16 ? 1.0f : kMqSplitOut;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  MqSmem<kStages>& sm = *reinterpret_cast<MqSmem<kStages>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using Smem = MqSmem<kStages, kRes>;
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -206,7 +268,7 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kMqKBlocks; ++s) {
+    for (int s = 0; s < kRes; ++s) {
       mbar_init(&sm.k_full[s], 2);   // leader's expect_tx arrive + peer's remote arrive
       mbar_init(&sm.k_empty[s], 1);  // one multicast tcgen05.commit (after the tile's last query)
     }
@@ -247,11 +309,13 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
       uint32_t phase = 0;
       for (int64_t tile = pair; tile < n_tiles; tile += n_pairs) {
         const int row0 = (int)(tile * kMqTileRays + rank * 128);
-        for (int kb = 0; kb < kMqKBlocks; ++kb) {
+        for (int kb = 0; kb < kRes; ++kb) {
           mbar_wait(&sm.k_empty[kb], phase ^ 1);  // the previous tile's last query is done with this slice
           if (leader) mbar_arrive_expect_tx(&sm.k_full[kb], 2 * kMqKBBytes);
           else mbar_arrive_cluster(&sm.k_full[kb], 0);
-          tma_load_2sm(sm.kt[kb], &tmap_k, &sm.k_full[kb], kb * 64, row0);
+          // f16f8 maps are byte-typed: hi blocks at 128 kb, the e4m3 copy of hi at 768 + 128 j
+          const int col = F8 ? (kb < 6 ? kb * 128 : 768 + (kb - 6) * 128) : kb * 64;
+          tma_load_2sm(sm.kt[kb], &tmap_k, &sm.k_full[kb], col, row0);
         }
         phase ^= 1;
       }
@@ -274,11 +338,21 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
         const int krow0 = (int)(tile * kMqTileRays + rank * 128);
         for (int b = 0; b < nq; ++b) {
           const int row0 = b * kMaxTokens + (int)rank * 128;
-          for (int kb = 0; kb < kMqKBlocks; ++kb) {
-            push(&tmap_q, kb * 64, row0);
-            if (SPLIT) {
-              push(&tmap_k, kFeat + kb * 64, krow0);
-              push(&tmap_q, kFeat + kb * 64, row0);
+          if (F8) {
+            for (int j = 0; j < 3; ++j) {
+              push(&tmap_q, (2 * j) * 128, row0);        // Qh block 2j     (fp16, 64 elements)
+              push(&tmap_q, (2 * j + 1) * 128, row0);    // Qh block 2j + 1
+              push(&tmap_q, 768 + j * 128, row0);        // Qh8 block j     (e4m3, 128 elements)
+              push(&tmap_k, 1152 + j * 128, krow0);      // Kl8 block j
+              push(&tmap_q, 1152 + j * 128, row0);       // Ql8 block j
+            }
+          } else {
+            for (int kb = 0; kb < kMqKBlocks; ++kb) {
+              push(&tmap_q, kb * 64, row0);
+              if (SPLIT) {
+                push(&tmap_k, kFeat + kb * 64, krow0);
+                push(&tmap_q, kFeat + kb * 64, row0);
+              }
             }
           }
         }
@@ -310,30 +384,72 @@ score_tc_mq_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
           mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
-          for (int kb = 0; kb < kMqKBlocks; ++kb) {
-            if (b == 0) mbar_wait(&sm.k_full[kb], kphase);
-            const uint32_t kh = smem_u32(sm.kt[kb]);
-            mbar_wait(&sm.q_full[stage], qphase);
-            tc_fence_after();
-            const int s_qh = stage;
-            group(tmem_d, smem_u32(sm.qs[s_qh]), kh, kb == 0);                     // Qh . Kh
-            next();
-            if (SPLIT) {
-              mbar_wait(&sm.q_full[stage], qphase);
+          if (F8) {
+            // main term in fp16 (K = 16 per MMA, 64-element blocks), cross terms in e4m3 (K = 32 per MMA, 128-element
+            // blocks): per j two Qh.Kh groups, then Qh8.Kl8 and Ql8.Kh8
+            auto group8 = [&](uint32_t tok, uint32_t key) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t dq = umma_desc_sw128(tok + k4 * 32);
+                const uint64_t dk = umma_desc_sw128(key + k4 * 32);
+                if (PASS == 1) mq_umma_f8(tmem_d, dq, dk, Cfg::kIdesc, 1u);
+                else mq_umma_f8(tmem_d, dk, dq, Cfg::kIdesc, 1u);
+              }
+            };
+            for (int j = 0; j < 3; ++j) {
+              for (int h = 0; h < 2; ++h) {
+                const int kb = 2 * j + h;
+                if (b == 0) mbar_wait(&sm.k_full[kb], kphase);
+                mbar_wait(&sm.q_full[stage], qphase);
+                tc_fence_after();
+                group(tmem_d, smem_u32(sm.qs[stage]), smem_u32(sm.kt[kb]), kb == 0);   // Qh . Kh
+                umma_commit_2sm(&sm.q_empty[stage]);
+                if (b == nq - 1) umma_commit_2sm(&sm.k_empty[kb]);
+                next();
+              }
+              mbar_wait(&sm.q_full[stage], qphase);                                     // Qh8
+              const int s_q8 = stage;
+              next();
+              mbar_wait(&sm.q_full[stage], qphase);                                     // Kl8
               tc_fence_after();
-              group(tmem_d, smem_u32(sm.qs[s_qh]), smem_u32(sm.qs[stage]), false);  // Qh . Kl
-              umma_commit_2sm(&sm.q_empty[s_qh]);
+              group8(smem_u32(sm.qs[s_q8]), smem_u32(sm.qs[stage]));                    // Qh8 . Kl8
+              umma_commit_2sm(&sm.q_empty[s_q8]);
               umma_commit_2sm(&sm.q_empty[stage]);
               next();
-              mbar_wait(&sm.q_full[stage], qphase);
+              if (b == 0) mbar_wait(&sm.k_full[6 + j], kphase);
+              mbar_wait(&sm.q_full[stage], qphase);                                     // Ql8
               tc_fence_after();
-              group(tmem_d, smem_u32(sm.qs[stage]), kh, false);                     // Ql . Kh
+              group8(smem_u32(sm.qs[stage]), smem_u32(sm.kt[6 + j]));                   // Ql8 . Kh8
               umma_commit_2sm(&sm.q_empty[stage]);
+              if (b == nq - 1) umma_commit_2sm(&sm.k_empty[6 + j]);
               next();
-            } else {
-              umma_commit_2sm(&sm.q_empty[s_qh]);                  // token stage free in both CTAs
             }
-            if (b == nq - 1) umma_commit_2sm(&sm.k_empty[kb]);     // key slice free once the tile's last query used it
+          } else {
+            for (int kb = 0; kb < kMqKBlocks; ++kb) {
+              if (b == 0) mbar_wait(&sm.k_full[kb], kphase);
+              const uint32_t kh = smem_u32(sm.kt[kb]);
+              mbar_wait(&sm.q_full[stage], qphase);
+              tc_fence_after();
+              const int s_qh = stage;
+              group(tmem_d, smem_u32(sm.qs[s_qh]), kh, kb == 0);                     // Qh . Kh
+              next();
+              if (SPLIT) {
+                mbar_wait(&sm.q_full[stage], qphase);
+                tc_fence_after();
+                group(tmem_d, smem_u32(sm.qs[s_qh]), smem_u32(sm.qs[stage]), false);  // Qh . Kl
+                umma_commit_2sm(&sm.q_empty[s_qh]);
+                umma_commit_2sm(&sm.q_empty[stage]);
+                next();
+                mbar_wait(&sm.q_full[stage], qphase);
+                tc_fence_after();
+                group(tmem_d, smem_u32(sm.qs[stage]), kh, false);                     // Ql . Kh
+                umma_commit_2sm(&sm.q_empty[stage]);
+                next();
+              } else {
+                umma_commit_2sm(&sm.q_empty[s_qh]);                  // token stage free in both CTAs
+              }
+              if (b == nq - 1) umma_commit_2sm(&sm.k_empty[kb]);     // key slice free once the tile's last query used it
+            }
           }
           umma_commit_2sm(&sm.tmem_full[acc]);
         }
@@ -472,16 +588,18 @@ __global__ void mq_ls_reduce_kernel(const double* __restrict__ part, int n_cta, 
   out[b * kMqLs + j] = a;
 }
 
-template <bool SPLIT>
+template <int FMT>
 int mq_make_map(CUtensorMap* map, const void* base, uint64_t rows) {
-  constexpr int row = MqCfg<SPLIT>::kRow;
-  return make_tmap_2d(map, SPLIT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, row,
-                      (uint64_t)row * 2, "score_tc_mq");
+  constexpr int row_bytes = MqCfg<FMT>::kRowBytes;
+  if (FMT == kFmtF16F8)  // mixed fp16 / e4m3 rows: a byte-typed map (128-byte wide boxes either way)
+    return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, base, rows, row_bytes, (uint64_t)row_bytes, "score_tc_mq");
+  return make_tmap_2d(map, FMT == kFmtF16x2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows,
+                      row_bytes / 2, (uint64_t)row_bytes, "score_tc_mq");
 }
 
 inline size_t mq_workspace(int nq) { return (size_t)(nq < 1 ? 1 : nq) * kMaxTokens * 2 * kFeat * 2 + 1024; }
 
-template <int PASS, bool SPLIT>
+template <int PASS, int FMT>
 int mq_launch(const void* kc, int64_t n_rays, const float* q, int nq, int n_img, float* pm, float* pz, const float* m,
               const float* z, float* scores, int64_t score_stride, const float* ori, const float* dir, double* ls_part,
               void* ws, size_t ws_bytes, cudaStream_t s) {
@@ -491,32 +609,39 @@ int mq_launch(const void* kc, int64_t n_rays, const float* q, int nq, int n_img,
   if (n_rays > (int64_t)INT32_MAX - 1024) { set_error("score_tc_mq: n_rays exceeds the TMA coordinate range"); return SIXDGS_EINVAL; }
   void* qb = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
   const int64_t nel = (int64_t)nq * kMaxTokens * kFeat;
-  if (SPLIT) mq_qprep_split_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(q, n_img, nq, (__half*)qb);
+  if (FMT == kFmtF16x2) mq_qprep_split_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(q, n_img, nq, (__half*)qb);
+  else if (FMT == kFmtF16F8) mq_qprep_f8_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(q, n_img, nq, (uint8_t*)qb);
   else mq_qprep_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(q, n_img, nq, (__nv_bfloat16*)qb);
   CUtensorMap mk, mq;
   int rc;
-  if ((rc = mq_make_map<SPLIT>(&mk, kc, (uint64_t)n_rays))) return rc;
-  if ((rc = mq_make_map<SPLIT>(&mq, qb, (uint64_t)nq * kMaxTokens))) return rc;
-  const size_t smem = sizeof(MqSmem<MqCfg<SPLIT>::kStages>) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(score_tc_mq_kernel<PASS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if ((rc = mq_make_map<FMT>(&mk, kc, (uint64_t)n_rays))) return rc;
+  if ((rc = mq_make_map<FMT>(&mq, qb, (uint64_t)nq * kMaxTokens))) return rc;
+  const size_t smem = sizeof(MqSmem<MqCfg<FMT>::kStages, MqCfg<FMT>::kResident>) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(score_tc_mq_kernel<PASS, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("score_tc_mq attr: %s", cudaGetErrorString(e)); return SIXDGS_ECUDA; }
-  score_tc_mq_kernel<PASS, SPLIT><<<kMqPairs * 2, kMqThreads, smem, s>>>(mk, mq, n_rays, n_img, nq, pm, pz, m, z, scores,
+  score_tc_mq_kernel<PASS, FMT><<<kMqPairs * 2, kMqThreads, smem, s>>>(mk, mq, n_rays, n_img, nq, pm, pz, m, z, scores,
                                                                           score_stride, ori, dir, ls_part);
   return check_launch("score_tc_mq");
 }
 
 }  // namespace
 
-// single-query entry points of the exact mode (api.cu dispatches impl 1 + SIXDGS_F16X2 here)
-int score_tc_split_pass1(const void* kc, int64_t n_rays, const float* q, int n_img, float* pm, float* pz, void* ws,
+// single-query entry points of the fp16-pair formats (api.cu dispatches impl 1 + SIXDGS_F16X2 / SIXDGS_F16F8 here)
+int score_tc_split_pass1(const void* kc, int k_dtype, int64_t n_rays, const float* q, int n_img, float* pm, float* pz, void* ws,
                          size_t ws_bytes, cudaStream_t s) {
-  return mq_launch<1, true>(kc, n_rays, q, 1, n_img, pm, pz, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, ws,
-                            ws_bytes, s);
+  if (k_dtype == SIXDGS_F16F8)
+    return mq_launch<1, kFmtF16F8>(kc, n_rays, q, 1, n_img, pm, pz, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, ws,
+                                   ws_bytes, s);
+  return mq_launch<1, kFmtF16x2>(kc, n_rays, q, 1, n_img, pm, pz, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, ws,
+                                 ws_bytes, s);
 }
-int score_tc_split_pass2(const void* kc, int64_t n_rays, const float* q, int n_img, const float* m, const float* z,
+int score_tc_split_pass2(const void* kc, int k_dtype, int64_t n_rays, const float* q, int n_img, const float* m, const float* z,
                          float* scores, void* ws, size_t ws_bytes, cudaStream_t s) {
-  return mq_launch<2, true>(kc, n_rays, q, 1, n_img, nullptr, nullptr, m, z, scores, n_rays, nullptr, nullptr, nullptr, ws,
-                            ws_bytes, s);
+  if (k_dtype == SIXDGS_F16F8)
+    return mq_launch<2, kFmtF16F8>(kc, n_rays, q, 1, n_img, nullptr, nullptr, m, z, scores, n_rays, nullptr, nullptr, nullptr,
+                                   ws, ws_bytes, s);
+  return mq_launch<2, kFmtF16x2>(kc, n_rays, q, 1, n_img, nullptr, nullptr, m, z, scores, n_rays, nullptr, nullptr, nullptr, ws,
+                                 ws_bytes, s);
 }
 size_t score_tc_split_workspace() { return mq_workspace(1); }
 
@@ -531,9 +656,21 @@ extern "C" int sixdgs_ls_partial_rows(void) { return kMqPairs * 2; }
 
 static int mq_check(const void* k_cache, int k_dtype, int64_t n_rays, int n_img) {
   SIXDGS_REQUIRE(k_cache, "null pointer");
-  SIXDGS_REQUIRE(k_dtype == SIXDGS_BF16 || k_dtype == SIXDGS_F16X2, "the batched path needs a bf16 or f16x2 key cache");
+  SIXDGS_REQUIRE(k_dtype == SIXDGS_BF16 || k_dtype == SIXDGS_F16X2 || k_dtype == SIXDGS_F16F8,
+                 "the batched path needs a bf16, f16x2 or f16f8 key cache");
   SIXDGS_REQUIRE(n_rays >= 1 && n_img >= 1 && n_img <= kMaxTokens, "bad sizes");
   return SIXDGS_OK;
+}
+
+template <int PASS>
+static int mq_dispatch(int k_dtype, const void* k_cache, int64_t n_rays, const float* q, int nq, int n_img, float* pm, float* pz,
+                       const float* m, const float* z, float* scores, int64_t score_stride, const float* ori, const float* dir,
+                       double* ls_part, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (k_dtype == SIXDGS_F16X2)
+    return mq_launch<PASS, kFmtF16x2>(k_cache, n_rays, q, nq, n_img, pm, pz, m, z, scores, score_stride, ori, dir, ls_part, ws, ws_bytes, s);
+  if (k_dtype == SIXDGS_F16F8)
+    return mq_launch<PASS, kFmtF16F8>(k_cache, n_rays, q, nq, n_img, pm, pz, m, z, scores, score_stride, ori, dir, ls_part, ws, ws_bytes, s);
+  return mq_launch<PASS, kFmtBf16>(k_cache, n_rays, q, nq, n_img, pm, pz, m, z, scores, score_stride, ori, dir, ls_part, ws, ws_bytes, s);
 }
 
 extern "C" int sixdgs_score_pass1_batch(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries,
@@ -542,11 +679,8 @@ extern "C" int sixdgs_score_pass1_batch(const void* k_cache, int k_dtype, int64_
   SIXDGS_REQUIRE(q && part_m && part_z, "null pointer");
   int rc = mq_check(k_cache, k_dtype, n_rays, n_img);
   if (rc) return rc;
-  if (k_dtype == SIXDGS_F16X2)
-    return mq_launch<1, true>(k_cache, n_rays, q, n_queries, n_img, part_m, part_z, nullptr, nullptr, nullptr, 0, nullptr,
-                              nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
-  return mq_launch<1, false>(k_cache, n_rays, q, n_queries, n_img, part_m, part_z, nullptr, nullptr, nullptr, 0, nullptr,
-                             nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+  return mq_dispatch<1>(k_dtype, k_cache, n_rays, q, n_queries, n_img, part_m, part_z, nullptr, nullptr, nullptr, 0, nullptr,
+                        nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 static int mq_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries, int n_img,
@@ -556,11 +690,8 @@ static int mq_pass2(const void* k_cache, int k_dtype, int64_t n_rays, const floa
   int rc = mq_check(k_cache, k_dtype, n_rays, n_img);
   if (rc) return rc;
   SIXDGS_REQUIRE(score_stride >= n_rays, "score_stride < n_rays");
-  if (k_dtype == SIXDGS_F16X2)
-    return mq_launch<2, true>(k_cache, n_rays, q, n_queries, n_img, nullptr, nullptr, m, z, scores, score_stride, ori, dir,
-                              ls_part, workspace, workspace_bytes, (cudaStream_t)stream);
-  return mq_launch<2, false>(k_cache, n_rays, q, n_queries, n_img, nullptr, nullptr, m, z, scores, score_stride, ori, dir,
-                             ls_part, workspace, workspace_bytes, (cudaStream_t)stream);
+  return mq_dispatch<2>(k_dtype, k_cache, n_rays, q, n_queries, n_img, nullptr, nullptr, m, z, scores, score_stride, ori, dir,
+                        ls_part, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int sixdgs_score_pass2_batch(const void* k_cache, int k_dtype, int64_t n_rays, const float* q, int n_queries,
@@ -590,4 +721,12 @@ extern "C" int sixdgs_split_keys(const float* k_f32, int64_t n, void* k_out, flo
   mq_split_keys_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, (cudaStream_t)stream>>>(k_f32, n, (__half*)k_out,
                                                                                          (unsigned int*)absmax);
   return check_launch("split_keys");
+}
+
+extern "C" int sixdgs_keys_f16x2_to_f16f8(void* keys, int64_t n, void* stream) {
+  SIXDGS_REQUIRE(keys, "null pointer");
+  SIXDGS_REQUIRE(n >= 0, "negative size");
+  if (n == 0) return SIXDGS_OK;
+  mq_keys_to_f8_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>((uint8_t*)keys, n);
+  return check_launch("keys_f16x2_to_f16f8");
 }

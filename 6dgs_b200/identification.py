@@ -29,7 +29,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from ._lib import BF16, F16X2, F32, SixdgsError
+from ._lib import BF16, F16F8, F16X2, F32, SixdgsError
 from .camera_up import CameraDirectionPredictor
 from .image_tokens import BackboneWrapper
 
@@ -158,8 +158,8 @@ class IdentificationModule(torch.nn.Module):
                                             self.backbone_wrapper.img_num_features + 14,
                                             self.backbone_wrapper.img_num_features, 1)
         self.score_impl = score_impl or os.environ.get("SIXDGS_SCORE_IMPL", "simt_fp32")
-        if self.score_impl not in ("simt_fp32", "simt_bf16", "tc_bf16", "tc_f16x2"):
-            raise ValueError("score_impl must be simt_fp32 | simt_bf16 | tc_bf16 | tc_f16x2")
+        if self.score_impl not in ("simt_fp32", "simt_bf16", "tc_bf16", "tc_f16x2", "tc_f16f8"):
+            raise ValueError("score_impl must be simt_fp32 | simt_bf16 | tc_bf16 | tc_f16x2 | tc_f16f8")
         self.attention_map_bytes_limit = attention_map_bytes_limit
         self.features_impl = os.environ.get("SIXDGS_FEATURES_IMPL", "auto")  # auto | simt | direct (TF32, direct-store epilogue)
         self._packed_cache = None
@@ -182,18 +182,18 @@ class IdentificationModule(torch.nn.Module):
 
     @property
     def _impl(self) -> int:
-        return ops.SCORE_TC if self.score_impl in ("tc_bf16", "tc_f16x2") else ops.SCORE_SIMT
+        return ops.SCORE_TC if self.score_impl in ("tc_bf16", "tc_f16x2", "tc_f16f8") else ops.SCORE_SIMT
 
     @property
     def _k_dtype(self) -> int:
-        return {"simt_fp32": F32, "tc_f16x2": F16X2}.get(self.score_impl, BF16)
+        return {"simt_fp32": F32, "tc_f16x2": F16X2, "tc_f16f8": F16F8}.get(self.score_impl, BF16)
 
     SPLIT_CHUNK = 1 << 20  # rays per fp32 staging chunk of the f16x2 build (1.6 GB of fp32 keys)
 
     @torch.no_grad()
     def build_key_cache(self, rays_ori, rays_dir, rays_rgb) -> RayKeyCache:
         """rays -> PE -> MLP -> k_proj -> K (once per scene / weight update; the reference redoes this per query)."""
-        if self.score_impl == "tc_f16x2":
+        if self.score_impl in ("tc_f16x2", "tc_f16f8"):
             # exact mode (the TF32 build is only good to 1.5e-3 on the keys): three-term split-fp16 tensor-core GEMMs
             # (csrc/features_x2.cu); SIXDGS_FEATURES_IMPL=simt keeps the fp32 FMA GEMMs, staged through fp32 chunks and
             # split into fp16 hi | lo rows (the cross-check of the tensor-core build)
@@ -212,6 +212,11 @@ class IdentificationModule(torch.nn.Module):
             if n and not float(absmax.item()) < ops.F16_MAX:  # one host read per scene build
                 raise SixdgsError(f"f16x2 key cache: max |16 k| = {float(absmax.item()):.4g} exceeds the fp16 range; "
                                   "use score_impl='simt_fp32' for keys of this magnitude")
+            if self.score_impl == "tc_f16f8":  # fast variant: e4m3 copies for the two cross terms, converted in place
+                if n and not float(absmax.item()) / 64.0 < 448.0:
+                    raise SixdgsError(f"f16f8 key cache: max |k| / 4 = {float(absmax.item()) / 64.0:.4g} exceeds the e4m3 "
+                                      "range; use score_impl='tc_f16x2'")
+                keys = ops.keys_to_f16f8(keys)
             return RayKeyCache(keys, n, ())
         # the throughput (bf16-key) modes build the cache with TF32 tensor-core GEMMs; the exact mode keeps fp32 FMA
         impl = ops.FEATURES_TC if (self.score_impl == "tc_bf16" and self.features_impl != "simt") else ops.FEATURES_SIMT

@@ -8,7 +8,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import BF16, F16X2, F32, FEAT, MAX_TOKENS, call, dptr, f32c, stream_ptr
+from ._lib import BF16, F16F8, F16X2, F32, FEAT, MAX_TOKENS, call, dptr, f32c, stream_ptr
 
 SCORE_SIMT = 0
 SCORE_TC = 1
@@ -253,8 +253,22 @@ def _kdtype(k: torch.Tensor) -> int:
         return BF16
     if k.dtype == torch.float16 and k.shape[-1] == 2 * FEAT:
         return F16X2
-    raise _lib.SixdgsError(f"key cache must be float32 / bfloat16 [n,{FEAT}] or float16 [n,{2 * FEAT}] (f16x2), "
+    if k.dtype == torch.uint8 and k.shape[-1] == 4 * FEAT:
+        return F16F8
+    raise _lib.SixdgsError(f"key cache must be float32 / bfloat16 [n,{FEAT}], float16 [n,{2 * FEAT}] (f16x2) or uint8 "
+                           f"[n,{4 * FEAT}] (f16f8), "
                            f"got {k.dtype} {tuple(k.shape)}")
+
+
+def keys_to_f16f8(keys_f16x2: torch.Tensor) -> torch.Tensor:
+    """f16x2 cache [n,768] fp16 -> f16f8 cache [n,1536] uint8, IN PLACE (the returned tensor aliases the input, whose
+    lo half is overwritten by the two e4m3 planes)"""
+    if _kdtype(keys_f16x2) != F16X2 or not keys_f16x2.is_contiguous():
+        raise _lib.SixdgsError("keys_to_f16f8 needs a contiguous f16x2 cache")
+    n = keys_f16x2.shape[0]
+    if n:
+        call("sixdgs_keys_f16x2_to_f16f8", dptr(keys_f16x2, torch.float16), n, stream_ptr())
+    return keys_f16x2.view(torch.uint8)
 
 
 F16X2_KEY_SCALE = 16.0   # stored f16x2 key = 16 k  (csrc/score_tc_mq.cu)

@@ -40,6 +40,10 @@ extern "C" {
 /* exact tensor-core key format: a row is [hi(384) | lo(384)] fp16 (1536 B) holding 16*k as hi + lo, hi = fp16(16 k),
  * lo = fp16(16 k - hi): 22 significant bits.  |k| must stay below 4094 (sixdgs_split_keys reports the maximum). */
 #define SIXDGS_F16X2 2
+/* fast variant of it: a row is [hi fp16 (768 B) | e4m3(hi / 64) (384 B) | e4m3(64 lo) (384 B)]; the two cross terms of the
+ * logit run as e4m3 MMAs at twice the rate (scores to ~3e-4 at a logit standard deviation of 6.5, growing linearly
+ * with it: inside the 1e-3 bar up to ~12).  Built from an F16X2 cache in place by sixdgs_keys_f16x2_to_f16f8. */
+#define SIXDGS_F16F8 3
 
 #define SIXDGS_FEAT 384      /* ray / image embedding width (DINOv2 ViT-S/14), backbone.py:17  */
 #define SIXDGS_MAX_TOKENS 256 /* 16x16 backbone grid, backbone.py:16                            */
@@ -180,12 +184,14 @@ int sixdgs_score_backward_dlogits(const float* k_f32, int64_t n_rays, const floa
  * max |16 k| over the converted rows so the caller can check the fp16 range (must stay < 65504). */
 int sixdgs_split_keys(const float* k_f32, int64_t n, void* k_out, float* absmax, void* stream);
 
+int sixdgs_keys_f16x2_to_f16f8(void* keys /* [n,768] fp16 in, [n,1536] bytes out, in place */, int64_t n, void* stream);
+
 /* ---- a11, several queries per key sweep -------- our_multihead_attention.py:4-12,70-79;
  *                                                  identification_module.py:80-82 (one call per image there)
  * Same mathematics as score_pass1 / score_pass2 with impl 1, for n_queries <= sixdgs_score_batch_max() queries that
  * share the key cache: q[n_queries, 256, 384] fp32, part_m / part_z [n_queries, sixdgs_score_batch_parts(), 256],
  * m / z [n_queries, 256], scores[n_queries, score_stride] (score_stride >= n_rays).  The keys cross HBM once per
- * pass for the whole batch.  k_dtype SIXDGS_BF16 or SIXDGS_F16X2; workspace >= sixdgs_score_batch_workspace(n_queries). */
+ * pass for the whole batch.  k_dtype SIXDGS_BF16, SIXDGS_F16X2 or SIXDGS_F16F8; workspace >= sixdgs_score_batch_workspace(n_queries). */
 int sixdgs_score_batch_max(void);
 int sixdgs_score_batch_parts(void);
 size_t sixdgs_score_batch_workspace(int n_queries);

@@ -251,6 +251,17 @@ def test_full_size_1m_gaussians_every_score_vs_fp64(sx, synthetic):
         c2w, _ = sx.ops.pose_tail(ori, dirs, idx, vals, up)
         c2w_ref, _ = sx.ops.pose_tail(ori, dirs, rt.indices, rt.values.float(), up)
         torch.testing.assert_close(c2w, c2w_ref, rtol=1e-4, atol=1e-4)
+    # the fast variant (e4m3 cross terms) on the same scene: the cache is converted in place
+    keys8 = sx.ops.keys_to_f16f8(cache.keys)
+    pm8, pz8 = sx.ops.score_pass1_batch(keys8, q)
+    mz8 = [sx.ops.score_merge(pm8[b * parts:(b + 1) * parts], pz8[b * parts:(b + 1) * parts], 256) for b in range(2)]
+    s8 = sx.ops.score_pass2_batch(keys8, q, torch.stack([x[0] for x in mz8]), torch.stack([x[1] for x in mz8]))
+    err8 = ((s8.double() - ref).abs() / ref).max().item()
+    report(f"1M Gaussians / {n} rays: max rel score err of tc_f16f8 vs fp64 over all rays = {err8:.3e}")
+    assert err8 < 1e-3, err8
+    for b in range(2):
+        _, idx8 = sx.ops.topk(s8[b], 100)
+        assert set(idx8.tolist()) == set(torch.topk(ref[b], 100).indices.tolist())
 
 
 # ------------------------------------------------------------------------------------ exact tensor-core key build
@@ -333,3 +344,56 @@ def test_f16x2_edge_cases(sx, synthetic):
     # a wrongly shaped cache is rejected before any launch
     with pytest.raises(sx.SixdgsError):
         sx.ops.score_pass1(torch.zeros(8, 384, dtype=torch.float16, device=DEV), torch.randn(256, 384, device=DEV), sx.ops.SCORE_TC)
+
+
+# ------------------------------------------------------------------------------------ fast variant: e4m3 cross terms
+@pytest.mark.parametrize("n_rays,n_img,q_scale", [(1, 256, 1.5), (300, 17, 5.0), (5513, 256, 10.0), (74 * 256 * 2 + 9, 256, 10.0)])
+def test_f16f8_kernel_vs_fp64(sx, n_rays, n_img, q_scale):
+    """score_impl="tc_f16f8": main term fp16, the two cross terms as e4m3 MMAs at twice the rate.  The cross terms are good
+    to ~5 %, so the error is ~0.05 x the fp16 rounding error and grows with the logit spread: inside the 1e-3 bar at logit
+    std 7 (this test), without the margin of f16x2.  Also: in-place conversion keeps the hi half, batched == single."""
+    gen = torch.Generator().manual_seed(n_rays + 1)
+    k = (torch.randn(n_rays, 384, generator=gen) * 0.7).to(DEV)
+    q = (torch.randn(3, n_img, 384, generator=gen) * q_scale).to(DEV)
+    k2 = sx.ops.split_keys(k)
+    hi = k2[:, :384].clone()
+    keys = sx.ops.keys_to_f16f8(k2)
+    assert keys.shape == (n_rays, 1536) and keys.dtype == torch.uint8
+    assert torch.equal(keys.view(torch.float16)[:, :384], hi)
+    qpad = torch.zeros(3, 256, 384, device=DEV)
+    qpad[:, :n_img] = q
+    pmb, pzb = sx.ops.score_pass1_batch(keys, qpad, n_img)
+    parts = pmb.shape[0] // 3
+    ms, zs = [], []
+    for b in range(3):
+        pm, pz = sx.ops.score_pass1(keys, q[b], sx.ops.SCORE_TC)
+        assert torch.equal(pm[:, :n_img], pmb[b * parts:(b + 1) * parts, :n_img])
+        m, z = sx.ops.score_merge(pm, pz, n_img)
+        ms.append(m)
+        zs.append(z)
+    sb = sx.ops.score_pass2_batch(keys, qpad, torch.stack(ms), torch.stack(zs), n_img)
+    worst = 0.0
+    for b in range(3):
+        s1, _ = sx.ops.score_pass2(keys, q[b], ms[b], zs[b], sx.ops.SCORE_TC)
+        assert torch.equal(s1, sb[b])
+        ref, L = fp64_scores(q[b], k)
+        worst = max(worst, rel_err(s1, ref))
+    report(f"f16f8 kernel vs fp64: n_rays {n_rays} n_img {n_img} logit std {L.std().item() if L.numel() > 1 else 0:.1f} "
+           f"max rel score err {worst:.3e}")
+    assert worst < 1e-3, worst
+
+
+def test_tc_f16f8_peaked_fixture_scores_topk_pose(sx, synthetic):
+    g = load_golden("id_module_peaked.npz")
+    r = load_golden("rays_small.npz")
+    idm = make_module(sx, synthetic, "tc_f16f8", q_gain=float(g["q_gain"]))
+    ori, dirs, rgb = cu(r["ori"]), cu(r["dirs"]), cu(r["rgb"])
+    mask = torch.ones(64, 64, dtype=torch.bool, device=DEV)
+    idx, vals, scores, up, _ = idm.test_image(cu(g["img"]), mask, ori, dirs, rgb)
+    err = rel_err(scores.cpu(), g["scores"])
+    report(f"tc_f16f8 vs reference, peaked fixture (logit std {float(g['logit_std']):.2f}): max rel score err {err:.3e}")
+    assert err < 1e-3, err
+    assert set(idx.cpu().tolist()) == set(g["topk_idx"].tolist())
+    cam = CameraInfo(0, g["R"].numpy(), g["T"].numpy(), np.float32(0.9), np.float32(0.9), g["img_u8"].numpy(), "", "0", 64, 64)
+    res, _, _, _, _ = sx.test_pose_estimation([cam], idm, ori, dirs, rgb, torch.tensor([0.0, 0.0, 1.0], device=DEV))
+    torch.testing.assert_close(torch.tensor(res[0]["pred_c2w"]), g["pred_c2w"], rtol=1e-4, atol=1e-4)

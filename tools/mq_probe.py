@@ -23,7 +23,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=12_000_000)
 ap.add_argument("--batches", default="8,4,1")
 ap.add_argument("--seconds", type=float, default=3.0)
-ap.add_argument("--variants", default="bf16_pq,bf16_mq,f16x2_mq")
+ap.add_argument("--variants", default="bf16_pq,bf16_mq,f16x2_mq,f16f8_mq")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -31,6 +31,7 @@ n = args.rays
 kf = torch.randn(n, 384, device=dev) * 0.5
 K16 = kf.to(torch.bfloat16)
 KX = sx.ops.split_keys(kf)
+K8 = sx.ops.keys_to_f16f8(sx.ops.split_keys(kf))
 del kf
 scores1 = torch.empty(n, device=dev)
 
@@ -60,7 +61,9 @@ def sm_clock():
 
 
 VARIANTS = {"bf16_pq": (per_query, K16, 768, 1, False), "bf16_mq": (multi_query, K16, 768, 1, True),
-            "f16x2_mq": (multi_query, KX, 1536, 3, True)}
+            "f16x2_mq": (multi_query, KX, 1536, 3, True),
+            # e4m3 cross terms: 3 MMA terms' worth of FLOPs issued as 2 term-units of tensor time
+            "f16f8_mq": (multi_query, K8, 1536, 3, True)}
 for B in [int(b) for b in args.batches.split(",")]:
     q = torch.randn(B, 256, 384, device=dev)
     sb = torch.empty(B, n, device=dev)
