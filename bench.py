@@ -416,6 +416,15 @@ def build_roofline(args, peaks, n_local, nq, burst, sustained, batched, sm_mhz, 
     return roof
 
 
+_T0 = time.perf_counter()
+
+
+def trace(msg):
+    """progress lines on stderr when SIXDGS_BENCH_TRACE=1 (every rank): where a multi-rank run spends its time"""
+    if os.environ.get("SIXDGS_BENCH_TRACE") == "1":
+        print(f"[bench r{os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
@@ -437,6 +446,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    trace("process group up")
     batched = args.score_impl.startswith("tc_") and not args.per_query_sweeps
 
     # ---------------- scene preparation (per scene; untimed for the metric, reported) ----------------
@@ -449,6 +459,7 @@ def main():
     ori, dirs, rgb = sx.generate_all_possible_rays(scene, max_ellipsoids=None, shard=shard)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
+    trace(f"rays generated ({ori.shape[0]})")
     import warnings
     torch.manual_seed(0)  # identical (random-init) backbone / head weights on every rank and every run
     backbone = sx.synthetic.SyntheticBackbone() if args.backbone == "synthetic" else sx.DinoV2ViTS14()
@@ -460,6 +471,7 @@ def main():
     cache = idm.build_key_cache(ori, dirs, rgb)
     torch.cuda.synchronize()
     t3 = time.perf_counter()
+    trace("key cache built")
     n_local = ori.shape[0]
     n_total = n_local
     if world > 1:
@@ -502,10 +514,12 @@ def main():
         lat_b1 = l0.elapsed_time(l1) / 10
         est._g = None
 
+    trace("latency figure done")
     # ---------------- warm-up, optional CUDA graph ----------------
     for _ in range(max(args.warmup, 3)):
         c2w, aux = query()
     torch.cuda.synchronize()
+    trace("eager warm-up done")
     time.sleep(1.0)  # let the GPU cool before the burst figure
     b1, b2 = time_score_kernels(sx, idm, cache, dev, 1, 3, B, batched)
     burst = {"pass1": b1, "pass2": b2}
@@ -528,6 +542,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    trace(f"graphs: {graph}")
     # ---------------- timed region: `value` ----------------
     sampler = ClockSampler(local)
     for _ in range(args.warmup):
@@ -551,6 +566,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = B * args.steps / (ms / 1e3)
+    trace("timed region done")
 
     # ---------------- eager per-stage breakdown (CUDA events, outside the timed region; what does not shrink with N) -----
     breakdown = None
@@ -591,6 +607,7 @@ def main():
            "h2d_bytes_per_step": int(img_host_q.numel()) * (world if own_only else 1),
            "d2h_bytes_per_step": 64 * B, "ms_per_step": e2e_ms / args.steps}
 
+    trace("e2e done")
     launches = (est.launches_per_query, est.launches_per_batch)
     peaks = load_peaks()
     roofline = build_roofline(args, peaks, n_local, B, burst, {"pass1": s1, "pass2": s2}, batched,
