@@ -334,7 +334,10 @@ def run_reference_arm(args):
     n_rays = expected_rays(args.gaussians)
     base = cpu_query_rate(args, n_rays, args.cpu_sample_ellipsoids, steps=max(1, args.steps), warmup=max(1, args.warmup))
     cfg = workload_config(args, n_rays, None)
-    cfg.update({"score_impl": "reference algorithm, fp32 torch CPU (ray MLP recomputed per query, no key cache)",
+    cfg.update({"workload": f"{args.gaussians} synthetic Gaussians (all valid ellipsoids, uncapped), {args.height}x{args.width} "
+                            "image, fp32 LS solve (BASELINE.json configs[2]): the reference algorithm on the host cores",
+                "solve": "topk",
+                "score_impl": "reference algorithm, fp32 torch CPU (ray MLP recomputed per query, no key cache)",
                 "queries_per_step": 1, "backbone": "none (random 256x398 tokens; the ViT is outside the timed CPU path)",
                 "backbone_matmul": None, "front_end": None, "score_sweeps": None, "parallelism": f"{base['cores']} host threads",
                 "l2": None, "sample_rays_per_step": base["sample_rays"], "sample_chunks": base["sample_chunks"]})
