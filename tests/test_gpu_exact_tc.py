@@ -397,3 +397,20 @@ def test_tc_f16f8_peaked_fixture_scores_topk_pose(sx, synthetic):
     cam = CameraInfo(0, g["R"].numpy(), g["T"].numpy(), np.float32(0.9), np.float32(0.9), g["img_u8"].numpy(), "", "0", 64, 64)
     res, _, _, _, _ = sx.test_pose_estimation([cam], idm, ori, dirs, rgb, torch.tensor([0.0, 0.0, 1.0], device=DEV))
     torch.testing.assert_close(torch.tensor(res[0]["pred_c2w"]), g["pred_c2w"], rtol=1e-4, atol=1e-4)
+
+
+def test_key_format_bytes_match_their_specification(sx):
+    """include/sixdgs.h documents the two fp16-pair key formats byte by byte; a torch emulation of that text must
+    reproduce the kernels' output bit for bit (values well inside the fp16 / e4m3 ranges)"""
+    gen = torch.Generator().manual_seed(12)
+    k = (torch.randn(1000, 384, generator=gen) * 0.7).to(DEV)
+    x = k * 16.0                                                   # SIXDGS_F16X2: hi = fp16(16 k), lo = fp16(16 k - hi)
+    hi = x.to(torch.float16)
+    lo = (x - hi.float()).to(torch.float16)
+    keys = sx.ops.split_keys(k)
+    assert torch.equal(keys[:, :384], hi) and torch.equal(keys[:, 384:], lo)
+    k8 = sx.ops.keys_to_f16f8(keys.clone())                        # SIXDGS_F16F8: [hi | e4m3(hi / 64) | e4m3(64 lo)]
+    assert torch.equal(k8[:, :768].contiguous().view(torch.float16), hi)
+    want_hi8 = (hi.float() / 64.0).to(torch.float8_e4m3fn).view(torch.uint8)
+    want_lo8 = (lo.float() * 64.0).to(torch.float8_e4m3fn).view(torch.uint8)
+    assert torch.equal(k8[:, 768:1152], want_hi8) and torch.equal(k8[:, 1152:], want_lo8)
