@@ -333,7 +333,7 @@ def score_pass2(k_cache: torch.Tensor, q: torch.Tensor, m: torch.Tensor, z: torc
     return scores, amap
 
 
-# ---- several queries per key sweep (EXPERIMENTAL, csrc/score_tc_mq.cu) ---------------------------------------
+# ---- several queries per key sweep (csrc/score_tc_mq.cu; bf16, f16x2 and f16f8 key caches) --------------------
 def score_batch_max() -> int:
     return int(_lib.load().sixdgs_score_batch_max())
 

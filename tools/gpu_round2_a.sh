@@ -7,4 +7,4 @@ LOG=gpurun_out/round2_a.log
 : > gpurun_out/parity_report.txt
 step() { echo "=== $*" | tee -a $LOG; timeout -k 10 "$@" 2>&1 | tail -40 | tee -a $LOG; echo "--- exit ${PIPESTATUS[0]}" | tee -a $LOG; }
 step 400 python -m pytest tests/test_gpu_exact_tc.py -q --timeout 300 -s
-SIXDGS_EXPERIMENTAL=1 step 200 python -m pytest tests/test_experimental.py -q --timeout 150 -k "multi_query"
+step 200 python -m pytest tests/test_gpu_pipeline.py -q --timeout 150 -k "multi_query"   # (was tests/test_experimental.py when this ran)
