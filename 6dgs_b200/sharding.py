@@ -178,6 +178,13 @@ class ShardedPoseEstimator:
         """this shard's partial softmax rows for every query of the batch"""
         b = self.backend
         nb, n_img = q.shape[0], q.shape[1]
+        if self.cache.n_rays == 0:
+            # a shard without rays (more ranks than blocks of ellipsoids): neutral statistics, (max, sum) = (-inf, 0),
+            # in the row layout the other ranks use, so the all-gather stays regular
+            rows = self.parts
+            pm = torch.full((nb * rows, _lib.MAX_TOKENS), float("-inf"), dtype=torch.float32, device=q.device)
+            return {"q": q, "valid": valid, "up": up, "pmz": torch.cat((pm, torch.zeros_like(pm)), 0), "n_img": n_img,
+                    "nb": nb, "rows": rows}
         if self.multi_query:
             q = q.contiguous()  # the batched kernel reads the batch as one [B*256, 384] matrix
             pm, pz = b.pass1_batch(self.cache.keys, q)  # [B * parts, 256], query-major like the loop below
@@ -244,6 +251,14 @@ class ShardedPoseEstimator:
         cand = None
         if self.world > 1:
             cand = torch.empty((nb, k, 7), dtype=torch.float32, device=self.ori.device)
+        if self.cache.n_rays == 0:  # empty shard: no scores, no local winners; its candidate rows are all -inf
+            ev = torch.empty(0, dtype=torch.float32, device=self.ori.device)
+            ei = torch.empty(0, dtype=torch.int64, device=self.ori.device)
+            if cand is not None:
+                for i in range(nb):
+                    b.candidates(ev, ei, self.ori, self.dirs, k, cand[i])
+            return [ev] * nb, [ei] * nb, cand
+
         def merged(i):
             # query i's rows: [rank g][query i][0..rows) -> group stride nb*rows, first row i*rows (no copies)
             return b.merge(pm, pz, st["n_img"], st["valid"][i] if st["valid"] is not None else None,
@@ -279,6 +294,8 @@ class ShardedPoseEstimator:
         """merged statistics -> scores + this shard's weighted least-squares system per query, ls_sys [B,13] float64"""
         b = self.backend
         nb, rows = st["nb"], st["rows"]
+        if self.cache.n_rays == 0:  # empty shard: contributes nothing to the sums
+            return torch.zeros((nb, 13), dtype=torch.float64, device=self.ori.device)
         groups = pmz.shape[0] // (2 * nb * rows)
         pm, pz = pmz, pmz[nb * rows:]
         mz = [b.merge(pm, pz, st["n_img"], st["valid"][i] if st["valid"] is not None else None, rows=rows, groups=groups,
@@ -333,6 +350,8 @@ class ShardedPoseEstimator:
         treated as B = 1; ``local`` as in ``query_batch``).  Returns False (and stays eager) if capture fails."""
         if img.dim() == 3:
             img, mask = img[None], mask[None]
+        if self.cache.n_rays == 0:
+            return False  # an empty shard has nothing worth capturing; it stays on the eager path
         cur = torch.cuda.current_stream()
         shard_front = self._shards_front(img.shape[0], local)
         g = {"shape": tuple(img.shape), "local": local, "k": k}

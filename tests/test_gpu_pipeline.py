@@ -359,3 +359,40 @@ def test_training_step_gradients_kernels_vs_torch_route(sx, synthetic, monkeypat
     for n_, gt in grads["torch"].items():
         gk = grads["kernels"][n_]
         assert (gk - gt).abs().max().item() <= 2e-3 * gt.abs().max().item() + floor, n_
+
+
+@pytest.mark.parametrize("impl,solve", [("simt_fp32", "topk"), ("tc_f16x2", "topk"), ("tc_f16x2", "weighted_ls")])
+def test_shard_without_rays_is_neutral_on_the_cuda_backend(sx, synthetic, impl, solve):
+    """ragged sharding on the CUDA backend (two shards emulated in one process, the second one EMPTY): neutral statistics,
+    all -inf candidate rows, a zero least-squares system -- the poses equal the unsharded ones; the empty shard declines
+    CUDA-graph capture"""
+    from conftest import load_golden
+    dev = "cuda"
+    g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
+    ori, dirs, rgb = r["ori"].to(dev), r["dirs"].to(dev), r["rgb"].to(dev)
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone(), score_impl=impl)
+    idm.load_state_dict(synthetic.synth_id_weights(seed=g["weight_seed"]), strict=False)
+    idm = idm.to(dev).eval().requires_grad_(False)
+    img = g["img"].to(dev)
+    imgs = torch.stack((img, img.flip(1)))
+    masks = torch.ones(2, 64, 64, dtype=torch.bool, device=dev)
+    ref, _ = sx.ShardedPoseEstimator(idm, ori, dirs, idm.build_key_cache(ori, dirs, rgb), solve=solve).query_batch(imgs, masks)
+    e3 = torch.empty(0, 3, device=dev)
+    shards = [sx.ShardedPoseEstimator(idm, ori, dirs, idm.build_key_cache(ori, dirs, rgb), 0, 2, solve=solve),
+              sx.ShardedPoseEstimator(idm, e3, e3.clone(), idm.build_key_cache(e3, e3.clone(), e3.clone()), 1, 2, solve=solve)]
+    assert shards[1].cache.n_rays == 0 and not shards[1].enable_cuda_graphs(imgs, masks)
+    sts = [s._stage1(imgs, masks) for s in shards]
+    assert sts[0]["pmz"].shape == sts[1]["pmz"].shape
+    pmz = torch.cat([st["pmz"] for st in sts])
+    if solve == "weighted_ls":
+        sys_sum = sum(s._stage2_weighted(pmz, st) for s, st in zip(shards, sts))
+        for s, st in zip(shards, sts):
+            c2w, _ = s._stage3_weighted(sys_sum, st)
+            torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)
+    else:
+        cands = [s._stage2(pmz, st, 100)[2] for s, st in zip(shards, sts)]
+        assert torch.isinf(cands[1][..., 0]).all() and (cands[1][..., 0] < 0).all()
+        allc = torch.cat(cands)
+        for s, st in zip(shards, sts):
+            c2w, _ = s._stage3(allc, st["up"], 100, st["nb"])
+            torch.testing.assert_close(c2w, ref, rtol=1e-5, atol=1e-5)

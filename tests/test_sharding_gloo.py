@@ -128,7 +128,8 @@ class OracleBatchBackend(OracleBackend):
         return torch.stack(c2w), torch.zeros(len(c2w), 8)
 
 
-def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=False, multi_query=False, solve="topk"):
+def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=False, multi_query=False, solve="topk",
+            empty_last=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -144,6 +145,8 @@ def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=Fal
     n = ori.shape[0]
     per = (n + world - 1) // world
     lo, hi = rank * per, min((rank + 1) * per, n)
+    if empty_last:  # ragged sharding: the last rank owns no rays at all
+        lo, hi = (0, n) if rank == 0 else (n, n)
     keys = torch.nn.functional.linear(oracle.ray_features(ori[lo:hi], dirs[lo:hi], rgb[lo:hi], w),
                                       w["attention.k_proj.weight"], w["attention.k_proj.bias"])
     cache = sx.RayKeyCache(keys, hi - lo, ())
@@ -158,7 +161,8 @@ def _worker(rank, world, port, out_path, nb=1, front_end="replicated", local=Fal
     c2w, _ = est.query_batch(imgs, masks, k=100, local=local)
     shards = front_end == "sharded" and nb % world == 0
     assert be.front_batches == [nb // world if shards else nb]  # the front end ran once, on this rank's share
-    assert getattr(be, "batch_calls", 0) == (2 if multi_query else 0)  # one call per pass for the whole batch
+    if hi > lo:
+        assert getattr(be, "batch_calls", 0) == (2 if multi_query else 0)  # one call per pass for the whole batch
     # every rank must hold the same poses
     gathered = [torch.empty_like(c2w) for _ in range(world)]
     dist.all_gather(gathered, c2w)
@@ -214,6 +218,29 @@ def test_two_rank_weighted_least_squares_one_allreduce(oracle, synthetic, tmp_pa
         watch = torch.nn.functional.normalize((wts[:, None] * r["dirs"]).sum(0), dim=0)
         torch.testing.assert_close(c2w[i, :3, 3], centre, rtol=1e-4, atol=1e-4)
         torch.testing.assert_close(c2w[i, :3, :3], torch.linalg.inv(oracle.make_rotation_mat(-watch, g["up"])), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("multi_query,solve", [(False, "topk"), (True, "topk"), (True, "weighted_ls")])
+def test_rank_without_rays_is_neutral(oracle, synthetic, tmp_path, multi_query, solve):
+    """ragged sharding: rank 1 owns no rays (more ranks than blocks of ellipsoids).  Its statistics are (-inf, 0), its
+    candidates all -inf, its least-squares system zero -- the poses equal the single-process oracle's"""
+    from conftest import load_golden
+    out = str(tmp_path / "c2w.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out, 2, "replicated", False, multi_query, solve, True), nprocs=2, join=True)
+    c2w = torch.load(out)
+    g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
+    w = synthetic.synth_id_weights(seed=g["weight_seed"])
+    fea = oracle.ray_features(r["ori"], r["dirs"], r["rgb"], w)
+    for i in range(2):
+        score, _ = oracle.attention_scores(g["tok_pe"] * (1.0 + 0.05 * i), fea, w, return_map=False)
+        if solve == "topk":
+            top = torch.topk(score, 100)
+            ref, _ = oracle.pose_tail(top.indices, top.values, r["ori"], r["dirs"], g["up"])
+            torch.testing.assert_close(c2w[i], ref, rtol=1e-4, atol=1e-4)
+        else:
+            centre = oracle.line_intersection(r["ori"], -r["dirs"], score / 256)
+            torch.testing.assert_close(c2w[i, :3, 3], centre, rtol=1e-4, atol=1e-4)
 
 
 def test_single_rank_path_uses_no_collective(sx, oracle, synthetic):
