@@ -1,4 +1,5 @@
-/* Plain-C use of libsixdgs.so (no Python, no torch): least-squares intersection of a few rays and a top-k.
+/* Plain-C use of libsixdgs.so (no Python, no torch): least-squares intersection of a few rays, a top-k, and the exact
+ * tensor-core ray score (fp32 keys -> f16x2 cache -> two passes) whose scores must sum to the number of tokens.
  * Build (from the repo root):
  *   gcc -std=c99 -Iinclude -I/usr/local/cuda/include examples/c_api_smoke.c -o c_api_smoke \
  *       -L6dgs_b200/csrc -lsixdgs -L/usr/local/cuda/lib64 -lcudart -lm -Wl,-rpath,$PWD/6dgs_b200/csrc
@@ -62,5 +63,40 @@ int main(void) {
   int64_t idx[2];
   cudaMemcpy(idx, d_i, sizeof idx, cudaMemcpyDeviceToHost);
   printf("top-2 indices = %lld %lld   expected 1 3\n", (long long)idx[0], (long long)idx[1]);
+
+  /* exact tensor-core score: 1000 pseudo-random keys, one query of 256 tokens */
+  enum { NR = 1000, NT = SIXDGS_MAX_TOKENS, D = SIXDGS_FEAT };
+  float* h_k = (float*)malloc(sizeof(float) * NR * D);
+  float* h_q = (float*)malloc(sizeof(float) * NT * D);
+  unsigned s = 12345u;
+  for (int i = 0; i < NR * D; ++i) { s = s * 1664525u + 1013904223u; h_k[i] = ((s >> 8) / 8388608.0f - 1.0f) * 0.7f; }
+  for (int i = 0; i < NT * D; ++i) { s = s * 1664525u + 1013904223u; h_q[i] = ((s >> 8) / 8388608.0f - 1.0f) * 3.0f; }
+  float *d_k, *d_q, *d_pm, *d_pz, *d_m, *d_z, *d_sc, *d_absmax;
+  void *d_keys, *d_sws;
+  const int parts = sixdgs_score_parts(1);
+  const size_t sws = sixdgs_score_workspace(1);
+  cudaMalloc((void**)&d_k, sizeof(float) * NR * D);
+  cudaMalloc((void**)&d_q, sizeof(float) * NT * D);
+  cudaMalloc(&d_keys, (size_t)NR * 2 * D * 2);               /* SIXDGS_F16X2: [hi(384) | lo(384)] fp16 per ray */
+  cudaMalloc((void**)&d_pm, sizeof(float) * parts * NT);
+  cudaMalloc((void**)&d_pz, sizeof(float) * parts * NT);
+  cudaMalloc((void**)&d_m, sizeof(float) * NT);
+  cudaMalloc((void**)&d_z, sizeof(float) * NT);
+  cudaMalloc((void**)&d_sc, sizeof(float) * NR);
+  cudaMalloc((void**)&d_absmax, sizeof(float));
+  cudaMalloc(&d_sws, sws);
+  cudaMemset(d_absmax, 0, sizeof(float));
+  cudaMemcpy(d_k, h_k, sizeof(float) * NR * D, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_q, h_q, sizeof(float) * NT * D, cudaMemcpyHostToDevice);
+  CK(sixdgs_split_keys(d_k, NR, d_keys, d_absmax, NULL));
+  CK(sixdgs_score_pass1(d_keys, SIXDGS_F16X2, NR, d_q, NT, d_pm, d_pz, 1, d_sws, sws, NULL));
+  CK(sixdgs_score_merge(d_pm, d_pz, parts, 1, 0, NT, NULL, d_m, d_z, NULL));
+  CK(sixdgs_score_pass2(d_keys, SIXDGS_F16X2, NR, d_q, NT, d_m, d_z, d_sc, NULL, 1, d_sws, sws, NULL));
+  float* h_sc = (float*)malloc(sizeof(float) * NR);
+  cudaMemcpy(h_sc, d_sc, sizeof(float) * NR, cudaMemcpyDeviceToHost);
+  double sum = 0.0;
+  for (int i = 0; i < NR; ++i) sum += h_sc[i];
+  printf("sum of the ray scores = %.4f   expected %d (every token's softmax sums to one)\n", sum, NT);
+  free(h_k); free(h_q); free(h_sc);
   return 0;
 }
