@@ -156,3 +156,14 @@ def test_peaked_softmax_fixture(oracle, synthetic, sx):
     kh, kl = split(k, torch.float16)
     e_x2 = err(qh @ kh.t() + qh @ kl.t() + ql @ kh.t())
     assert e_bf16 > 1e-2 and e_fp16 > 2e-3 and e_x2 < 1e-5, (e_bf16, e_fp16, e_x2)
+    # the fast variant (tc_f16f8) with the kernel's own scales: stored key 16 k, stored query 64 c q (c = log2e / sqrt(384)
+    # cancels in this study), cross-term operands e4m3(hi / 64) and e4m3(64 lo) -- products land on the main term's scale
+    def f8(x):
+        return x.float().to(torch.float8_e4m3fn).double()
+
+    Qh, Ql = split(q * 64.0, torch.float16)
+    Kh, Kl = split(k * 16.0, torch.float16)
+    acc = Qh @ Kh.t() + f8(Qh / 64.0) @ f8(Kl * 64.0).t() + f8(Ql * 64.0) @ f8(Kh / 64.0).t()
+    e_f8 = err(acc / 1024.0)
+    assert e_x2 < e_f8 < 1e-3, e_f8          # inside the bar here (logit std 6.5), 0.05 x the fp16 error, no margin at 3 x the spread
+    assert e_f8 < 0.1 * e_fp16
