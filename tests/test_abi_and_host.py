@@ -280,3 +280,53 @@ def test_local_vit_is_name_compatible_with_the_dinov2_vits14_checkpoint(sx, tmp_
     res = model.load_state_dict(fake, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     torch.testing.assert_close(model.state_dict()["blocks.7.attn.qkv.weight"], fake["blocks.7.attn.qkv.weight"])
+
+
+def test_sharded_front_end_record_roundtrip(sx):
+    """the (q, up, validity) record a rank all-gathers for its images: padded to a multiple of 64 floats (every q block
+    of the gathered buffer stays 256-byte aligned), unpacked views equal the inputs, q rows stay contiguous"""
+    est = sx.ShardedPoseEstimator.__new__(sx.ShardedPoseEstimator)  # the helpers need no state
+    gen = torch.Generator().manual_seed(0)
+    for bl, n_img, d in ((1, 256, 384), (3, 256, 384), (2, 7, 16)):
+        q = torch.randn(bl, n_img, d, generator=gen)
+        up = torch.nn.functional.normalize(torch.randn(bl + 2, 3, generator=gen), dim=-1)  # backends may return extra rows
+        valid = (torch.rand(bl, n_img, generator=gen) > 0.3).to(torch.uint8)
+        rec = est._pack_front(q, up, valid)
+        assert rec.shape == (bl, est._record_len(n_img, d)) and rec.shape[1] % 64 == 0
+        q2, up2, v2 = est._unpack_front(torch.cat((rec, rec)), n_img, d)  # as if gathered from two ranks
+        assert torch.equal(q2[:bl], q) and torch.equal(q2[bl:], q) and q2[1 if bl > 1 else 0].is_contiguous()
+        assert torch.equal(up2[:bl], up[:bl]) and torch.equal(v2[:bl], valid)
+        rec_none = est._pack_front(q, up, None)  # no mask information: every token valid
+        assert est._unpack_front(rec_none, n_img, d)[2].all()
+
+
+def test_eval_driver_camera_conversion_roundtrip():
+    """cameras.json stores (c2w rotation, camera position); CameraInfo wants (R = c2w rotation, T = w2c translation);
+    test.py:47-67 turns that back into the pose: position and rotation must survive the round trip"""
+    import importlib
+    import json
+    import tempfile
+    drv = importlib.import_module("6dgs_b200.eval_driver")
+    gen = torch.Generator().manual_seed(3)
+    cams = []
+    for i in range(4):
+        qv = torch.nn.functional.normalize(torch.randn(4, generator=gen), dim=0)
+        w, x, y, z = qv.tolist()
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        pos = (torch.randn(3, generator=gen) * 3).numpy()
+        cams.append({"id": i, "img_name": f"im{i}", "width": 640, "height": 480, "position": pos.tolist(),
+                     "rotation": R.tolist(), "fx": 500.0, "fy": 510.0})
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
+        json.dump(cams, fh)
+    infos = drv.cameras_from_json(fh.name, None, load_images=False)
+    os.unlink(fh.name)
+    for c, info in zip(cams, infos):
+        w2c = np.eye(4)
+        w2c[:3, :3] = info.R.T            # test.py:47-52: w2c rotation = R^T, translation = T
+        w2c[:3, 3] = info.T
+        c2w = np.linalg.inv(w2c)
+        np.testing.assert_allclose(c2w[:3, 3], c["position"], atol=1e-5)
+        np.testing.assert_allclose(c2w[:3, :3], c["rotation"], atol=1e-5)
+        assert abs(drv.focal2fov(c["fx"], 640) - float(info.FovX)) < 1e-6 and (info.width, info.height) == (640, 480)
