@@ -330,3 +330,63 @@ def test_eval_driver_camera_conversion_roundtrip():
         np.testing.assert_allclose(c2w[:3, 3], c["position"], atol=1e-5)
         np.testing.assert_allclose(c2w[:3, :3], c["rotation"], atol=1e-5)
         assert abs(drv.focal2fov(c["fx"], 640) - float(info.FovX)) < 1e-6 and (info.width, info.height) == (640, 480)
+
+
+def test_c_abi_argument_validation_needs_no_gpu(sx):
+    """Error behaviour of the C ABI (include/sixdgs.h "Conventions"): bad arguments come back as SIXDGS_EINVAL (-1) /
+    SIXDGS_EWORKSPACE (-3) with a message naming the entry point, BEFORE any CUDA call -- so it is checkable here.  The
+    pointers are fake non-null device addresses that these paths never dereference.  Also the pure-host size queries."""
+    import ctypes
+    lib = sx._lib.load()
+    P = ctypes.c_void_p(4096)
+    EINVAL, EWS = -1, -3
+    F32, BF16, F16X2, F16F8 = 0, 1, 2, 3
+
+    def err():
+        return lib.sixdgs_last_error().decode()
+
+    assert lib.sixdgs_degrade_mask(None, 10, 50, P, None, None) == EINVAL and "sixdgs_degrade_mask" in err()
+    assert lib.sixdgs_topk(None, 100, 10, P, P, P, 1 << 20, None) == EINVAL
+    assert lib.sixdgs_topk(P, 100, 0, P, P, P, 1 << 20, None) == EINVAL and "k must be in [1, 1024]" in err()
+    assert lib.sixdgs_topk(P, 100, 2000, P, P, P, 1 << 20, None) == EINVAL
+    assert lib.sixdgs_topk(P, 5, 10, P, P, P, 1 << 20, None) == EINVAL and "out of range" in err()  # torch.topk raises too
+    assert lib.sixdgs_topk(P, 1 << 20, 10, P, P, P, 8, None) == EWS
+    # score: dtype / impl combinations, token count
+    assert lib.sixdgs_score_pass1(P, 99, 1000, P, 256, P, P, 1, P, 1 << 22, None) == EINVAL and "k_dtype" in err()
+    assert lib.sixdgs_score_pass1(P, F32, 1000, P, 256, P, P, 1, P, 1 << 22, None) == EINVAL     # tensor cores need bf16 / f16x2 / f16f8
+    assert lib.sixdgs_score_pass1(P, F16X2, 1000, P, 256, P, P, 0, P, 1 << 22, None) == EINVAL   # the fp16-pair formats need impl 1
+    assert lib.sixdgs_score_pass1(P, F16F8, 1000, P, 256, P, P, 0, P, 1 << 22, None) == EINVAL
+    assert lib.sixdgs_score_pass1(P, BF16, 1000, P, 300, P, P, 1, P, 1 << 22, None) == EINVAL and "n_img" in err()
+    assert lib.sixdgs_score_pass1(P, BF16, 0, P, 256, P, P, 1, P, 1 << 22, None) == EINVAL
+    assert lib.sixdgs_score_pass2(P, BF16, 1000, P, 256, P, P, P, P, 1, P, 1 << 22, None) == EINVAL and "attention map" in err()
+    # batched score: at most 8 queries per launch, workspace, score stride
+    ws8 = lib.sixdgs_score_batch_workspace(8)
+    assert lib.sixdgs_score_batch_max() == 8 and lib.sixdgs_score_batch_parts() == 74 == lib.sixdgs_score_parts(1)
+    assert ws8 == 8 * 256 * 768 * 2 + 1024 and lib.sixdgs_score_workspace(1) == 256 * 768 * 2 + 1024 and lib.sixdgs_score_workspace(0) == 0
+    assert lib.sixdgs_score_pass1_batch(P, F16X2, 1000, P, 9, 256, P, P, P, ws8, None) == EINVAL and "n_queries" in err()
+    assert lib.sixdgs_score_pass1_batch(P, F16X2, 1000, P, 8, 256, P, P, None, 0, None) == EWS
+    assert lib.sixdgs_score_pass1_batch(P, F32, 1000, P, 8, 256, P, P, P, ws8, None) == EINVAL
+    assert lib.sixdgs_score_pass2_batch(P, F16F8, 1000, P, 2, 256, P, P, P, 999, P, ws8, None) == EINVAL and "score_stride" in err()
+    assert lib.sixdgs_score_pass2_batch_ls(P, F16X2, 1000, P, 2, 256, P, P, P, 1000, None, P, P, P, P, ws8, None) == EINVAL
+    assert lib.sixdgs_ls_partial_rows() == 148 and lib.sixdgs_score_backward_parts() == 296
+    # least-squares solve, pose tail
+    assert lib.sixdgs_ls_solve(P, 0, 1.0, None, P, None, None, None, None, None) == EINVAL
+    assert lib.sixdgs_ls_solve(P, 2, 1.0, None, None, None, P, None, None, None) == EINVAL and "camera-up" in err()
+    assert lib.sixdgs_pose_tail(P, P, 3, P, P, 2000, P, P, None, None) == EINVAL
+    assert lib.sixdgs_pose_tail(P, P, 2, P, P, 100, P, P, None, None) == EINVAL and "ray_stride" in err()
+    # ray generation / features
+    assert lib.sixdgs_raygen_fill(P, P, P, P, 4, 16, P, 10, P, 50, 1000, 0, P, P, P, P, None, None, None) == EINVAL and "sh_degree" in err()
+    assert lib.sixdgs_raygen_fill(P, P, P, P, 3, 9, P, 10, P, 50, 1000, 0, P, P, P, P, None, None, None) == EINVAL and "coefficients" in err()
+    assert lib.sixdgs_raygen_fill(P, P, P, P, 3, 16, P, 10, P, 50, 5000, 0, P, P, P, P, None, None, None) == EINVAL and "resolution" in err()
+    assert lib.sixdgs_raygen_cells(None, None, 10, 50, P, None) == EINVAL
+    assert lib.sixdgs_raygen_compact(P, P, P, 10, P, None, None, None, P, P, None, None, None) == EINVAL  # dir without its source
+    x2ws = lib.sixdgs_ray_features_x2_workspace(1 << 20)
+    assert x2ws == (1 << 17) * 2 * (704 + 512 + 384) * 2 + 1024
+    assert lib.sixdgs_ray_features_x2(P, P, P, 1000, *([P] * 10), P, None, P, 16, None) == EWS
+    assert lib.sixdgs_ray_features_x2(P, P, P, 1000, *([P] * 9), None, P, None, P, x2ws, None) == EINVAL
+    assert lib.sixdgs_split_keys(None, 10, P, None, None) == EINVAL and lib.sixdgs_split_keys(P, 0, P, None, None) == 0
+    assert lib.sixdgs_keys_f16x2_to_f16f8(None, 10, None) == EINVAL and lib.sixdgs_keys_f16x2_to_f16f8(P, 0, None) == 0
+    assert lib.sixdgs_score_backward_dlogits(P, 1000, P, 256, P, P, P, P, P, P, 10, None) == EINVAL and "ldt" in err()
+    # empty inputs are not errors
+    assert lib.sixdgs_degrade_mask(P, 0, 50, P, None, None) == 0 and lib.sixdgs_raygen_cells(P, None, 0, 50, P, None) == 0
+    assert lib.sixdgs_version() >= 200
