@@ -88,11 +88,10 @@ class ShardedPoseEstimator:
     fragile; two eager launches per query cost ~10 us).
 
     ``front_end``: what the ranks do with the image front end (resize, backbone, q projection, up head) of a
-    batch.  "replicated" (default): every rank runs it for the whole batch -- no extra collective, but the
-    replicated milliseconds do not shrink with the world size.  "sharded": when the batch size is a multiple of
-    the world size each rank runs it for its B/world images only and one more all-gather (q rows, up vector and
-    token validity, ~394 KB per query) hands every rank the whole batch; other batch sizes fall back to
-    "replicated".  With ``query_batch(..., local=True)`` the caller passes just this rank's images, so only
+    batch.  "sharded" (default; a no-op on one rank): when the batch size is a multiple of the world size each rank
+    runs it for its B/world images only and one more all-gather (q rows, up vector and token validity, ~394 KB per
+    query) hands every rank the whole batch; other batch sizes fall back to "replicated": every rank runs it for the
+    whole batch -- no extra collective, but the replicated milliseconds do not shrink with the world size.  With ``query_batch(..., local=True)`` the caller passes just this rank's images, so only
     those cross PCIe.
 
     ``multi_query`` (tensor-core path only; default: on for it): score the whole batch in one sweep over the key cache
@@ -107,7 +106,7 @@ class ShardedPoseEstimator:
     tensor-core kernel (multi_query)."""
 
     def __init__(self, idm, rays_ori: torch.Tensor, rays_dir: torch.Tensor, cache, rank: int = 0, world: int = 1,
-                 backend=None, group=None, front_end: str = "replicated", multi_query: Optional[bool] = None,
+                 backend=None, group=None, front_end: str = "sharded", multi_query: Optional[bool] = None,
                  solve: str = "topk"):
         if front_end not in ("replicated", "sharded"):
             raise ValueError(f"front_end must be 'replicated' or 'sharded', got {front_end!r}")
