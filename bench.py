@@ -118,6 +118,8 @@ class ClockSampler:
         self.p = None
 
     def start(self):
+        if self.gpu is None:
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
@@ -126,10 +128,17 @@ class ClockSampler:
 
     def stop(self):
         if self.p is None:
+            self.f.close()
+            os.unlink(self.f.name)
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
-        self.p.terminate()
-        self.p.wait()
+        for stop in (self.p.terminate, self.p.kill):  # never let a stuck nvidia-smi hold the bench
+            stop()
+            try:
+                self.p.wait(timeout=5)
+                break
+            except subprocess.TimeoutExpired:
+                continue
         self.f.flush()
         rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
@@ -547,7 +556,7 @@ def main():
 
     trace(f"graphs: {graph}")
     # ---------------- timed region: `value` ----------------
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local if rank == 0 else None)  # the line is rank 0's; N polling nvidia-smi loops only contend
     for _ in range(args.warmup):
         step()
     barrier()
