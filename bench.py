@@ -456,7 +456,9 @@ def main():
         torch.set_float32_matmul_precision("high")
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective that does not complete in 5 min aborts the job (NCCL watchdog) instead of hanging the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
     trace("process group up")
     batched = args.score_impl.startswith("tc_") and not args.per_query_sweeps
