@@ -26,6 +26,8 @@ def test_reference_arm_prints_contract_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and "extrapolated" in cb["sample"] and cb["value"] == line["value"]
     assert line["config"]["workload"].startswith("2000 synthetic Gaussians") and line["scaling"] == "strong"
+    shipped = cb["as_shipped"]  # one query / one ray-generation call of the reference as shipped (1000-ellipsoid cap)
+    assert 0 < shipped["rays"] <= cb["sample_rays"] and shipped["ms_per_query"] > 0 and shipped["raygen_s_per_call"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
