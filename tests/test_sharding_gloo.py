@@ -1,4 +1,4 @@
-"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo processes run
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 (and one world_size-4) gloo processes run
 ShardedPoseEstimator with an oracle-backed compute backend (tests may use the oracle; the package
 only ships the CUDA backend) and must reproduce the single-process oracle pose exactly."""
 import importlib
@@ -196,6 +196,31 @@ def test_two_rank_sharded_query_matches_single_process(oracle, synthetic, tmp_pa
         ref_i, _ = oracle.pose_tail(top.indices, top.values, r["ori"], r["dirs"], g["up"])
         torch.testing.assert_close(c2w[i], ref_i, rtol=1e-4, atol=1e-4)
         assert not torch.allclose(c2w[i], c2w[0])
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("solve", ["topk", "weighted_ls"])
+def test_four_rank_bench_configuration(oracle, synthetic, tmp_path, solve):
+    """the shape of `bench.py --gpus 4`: 8 queries per batch, sharded front end with each rank handed its own 2 images,
+    batched sweeps -- every rank ends with the 8 poses of the unsharded oracle"""
+    from conftest import load_golden
+    out = str(tmp_path / "c2w.pt")
+    nb = 8
+    mp.spawn(_worker, args=(4, _free_port(), out, nb, "sharded", True, True, solve), nprocs=4, join=True)
+    c2w = torch.load(out)
+    assert c2w.shape == (nb, 4, 4)
+    g, r = load_golden("id_module.npz"), load_golden("rays_small.npz")
+    w = synthetic.synth_id_weights(seed=g["weight_seed"])
+    fea = oracle.ray_features(r["ori"], r["dirs"], r["rgb"], w)
+    for i in range(nb):
+        score, _ = oracle.attention_scores(g["tok_pe"] * (1.0 + 0.05 * i), fea, w, return_map=False)
+        if solve == "topk":
+            top = torch.topk(score, 100)
+            ref, _ = oracle.pose_tail(top.indices, top.values, r["ori"], r["dirs"], g["up"])
+            torch.testing.assert_close(c2w[i], ref, rtol=1e-4, atol=1e-4)
+        else:
+            centre = oracle.line_intersection(r["ori"], -r["dirs"], score / 256)
+            torch.testing.assert_close(c2w[i, :3, 3], centre, rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.timeout(300)
