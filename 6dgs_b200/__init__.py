@@ -15,6 +15,7 @@ from .evaluate import test_pose_estimation  # noqa: F401
 from .identification import IdentificationModule, MultiHeadAttention, RayKeyCache, RayPreprocessor  # noqa: F401
 from .image_tokens import BackboneWrapper, DinoV2ViTS14, create_backbone  # noqa: F401
 from .camera_up import CameraDirectionPredictor  # noqa: F401
+from .losses import DistanceBasedScoreLoss, best_one_to_one_rays_selector  # noqa: F401
 from .pose_solve import (compute_line_intersection_impl2, exclude_negatives, make_rotation_mat,  # noqa: F401
                          pose_from_topk)
 from .raygen import generate_all_possible_rays, quadricell_cells  # noqa: F401

@@ -121,6 +121,9 @@ def main(argv=None):
     ap.add_argument("--backbone", default="dino", choices=["dino", "synthetic"],
                     help="synthetic = the deterministic stand-in used by the fixtures (no DINOv2 weights offline)")
     ap.add_argument("--seed", type=int, default=55176280)  # pretrain_eval_attention.py:183
+    ap.add_argument("--oracle_rays", action="store_true",
+                    help="also run the reference driver's first pass (pretrain_eval_attention.py:100-120): poses from the "
+                         "top-100 distance-based TARGET scores, score loss and top-100 recall of the predictions")
     args = ap.parse_args(argv)
     if args.dinov2:
         os.environ["SIXDGS_DINOV2_WEIGHTS"] = args.dinov2
@@ -137,10 +140,15 @@ def main(argv=None):
     idm, trained = load_id_module(sx, args.exp_path, args.weights, args.score_impl, dev, backbone)
     rays = sx.generate_all_possible_rays(scene, sample_quadricell_targets=50,
                                          max_ellipsoids=None if args.max_ellipsoids == 0 else args.max_ellipsoids)
-    results, t_err, a_err, _, _ = sx.test_pose_estimation(test_cams, idm, *rays, model_up,
-                                                          sequence_id=os.path.basename(os.path.normpath(args.exp_path or ply)))
+    seq = os.path.basename(os.path.normpath(args.exp_path or ply))
+    oracle_rays = None
+    if args.oracle_rays:
+        _, o_t, o_a, o_loss, o_recall = sx.test_pose_estimation(test_cams, idm, *rays, model_up, sequence_id=seq,
+                                                                loss_fn=sx.DistanceBasedScoreLoss())
+        oracle_rays = {"avg_translation_error": o_t, "avg_angular_error": o_a, "avg_score_loss": o_loss, "recall": o_recall}
+    results, t_err, a_err, _, _ = sx.test_pose_estimation(test_cams, idm, *rays, model_up, sequence_id=seq)
     out = {"results": results, "avg_translation_error": t_err, "avg_angular_error": a_err, "n_rays": int(rays[0].shape[0]),
-           "trained_weights": trained, "point_cloud": ply}
+           "trained_weights": trained, "point_cloud": ply, "oracle_rays": oracle_rays}
     with open(args.out, "w") as fh:
         json.dump(out, fh)
     print(f"[eval_driver] {len(results)} frames, {rays[0].shape[0]} rays -> {args.out}: "

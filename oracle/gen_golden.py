@@ -216,7 +216,8 @@ def gen_line_intersection():
     npz("line_intersection.npz", **cases)
 
 
-def gen_pose(idm, ori, dirs, rgb):
+def pose_cameras():
+    """the three fixture cameras (random rigid poses, one RGBA image) of pose.npz / loss.npz"""
     g = torch.Generator().manual_seed(31)
     cams, imgs = [], []
     for i in range(3):
@@ -234,6 +235,11 @@ def gen_pose(idm, ori, dirs, rgb):
         imgs.append(img)
         cams.append(CameraInfo(uid=i, R=R, T=T, FovY=np.float32(0.9), FovX=np.float32(0.9), image=img,
                                image_path="", image_name=str(i), width=64, height=64))
+    return cams, imgs
+
+
+def gen_pose(idm, ori, dirs, rgb):
+    cams, imgs = pose_cameras()
     results, t_err, a_err, _, _ = test_pose_estimation(cams, idm, ori, dirs, rgb,
                                                        torch.tensor([0.0, 0.0, 1.0]))
     npz("pose.npz", R=np.stack([c.R for c in cams]), T=np.stack([c.T for c in cams]),
@@ -244,6 +250,44 @@ def gen_pose(idm, ori, dirs, rgb):
         avg_t_err=t_err, avg_ang_err=a_err)
 
 
+def fixture_id_module():
+    """the identification module of id_module.npz (weights seed 3), without rewriting that fixture"""
+    idm = IdentificationModule("dino").eval()
+    missing = idm.load_state_dict(synthetic.synth_id_weights(seed=3), strict=False)
+    assert not missing.unexpected_keys, missing.unexpected_keys
+    return idm
+
+
+def gen_loss(idm, ori, dirs, rgb):
+    """DistanceBasedScoreLoss / best_one_to_one_rays_selector of the UNMODIFIED reference on the fixture rays and the
+    pose.npz cameras, and test_pose_estimation in its "oracle rays" mode (loss_fn given: the pose is solved from the
+    top-100 TARGET scores, test.py:110-142)."""
+    from pose_estimation.distance_based_loss import DistanceBasedScoreLoss, best_one_to_one_rays_selector
+    from utils.graphics_utils import fov2focal
+    cams, _ = pose_cameras()
+    pred = torch.from_numpy(np.load(os.path.join(OUT, "id_module.npz"))["scores"])
+    out = {}
+    for i, cam in enumerate(cams):
+        w2c = torch.eye(4)
+        w2c[:3, :3] = torch.from_numpy(cam.R).T
+        w2c[:3, 3] = torch.from_numpy(cam.T)
+        pose = torch.inverse(w2c)
+        f = fov2focal(cam.FovX, cam.width)
+        K = torch.tensor([[f, 0.0, cam.width / 2], [0.0, fov2focal(cam.FovY, cam.height), cam.height / 2], [0.0, 0.0, 1.0]])
+        for shape in ((800, 800), (480, 640)):
+            _, inside, tgt, tgt_d = best_one_to_one_rays_selector(K, pose, shape, dirs, ori, backbone_wh=(16, 16))
+            out[f"inside{i}_{shape[0]}"] = inside
+        loss, target = DistanceBasedScoreLoss()(pred, pose, K, ori, dirs, 256, (16, 16), model_up=None)
+        out.update({f"pose{i}": pose, f"K{i}": K, f"target_raw{i}": tgt, f"target_dist{i}": tgt_d, f"target{i}": target,
+                    f"loss{i}": loss})
+    results, t_err, a_err, avg_loss, avg_recall = test_pose_estimation(cams, idm, ori, dirs, rgb, torch.tensor([0.0, 0.0, 1.0]),
+                                                                       loss_fn=DistanceBasedScoreLoss())
+    npz("loss.npz", pred=pred, pred_c2w=np.array([r["pred_c2w"] for r in results], dtype=np.float32),
+        scores_loss=np.array([r["scores_loss"] for r in results], dtype=np.float32),
+        recall=np.array([r["recall"] for r in results], dtype=np.float32), avg_t_err=t_err, avg_ang_err=a_err,
+        avg_loss=avg_loss, avg_recall=avg_recall, **out)
+
+
 if __name__ == "__main__":
     if "--only-ply" in sys.argv:
         gen_ply()
@@ -251,6 +295,10 @@ if __name__ == "__main__":
     if "--only-peaked" in sys.argv:  # add the peaked-softmax fixture without touching the others (rays from the fixture)
         g = np.load(os.path.join(OUT, "rays_small.npz"))
         gen_id_module_peaked(*(torch.from_numpy(g[k]) for k in ("ori", "dirs", "rgb")))
+        sys.exit(0)
+    if "--only-loss" in sys.argv:  # add the loss / oracle-rays fixture without touching the others
+        g = np.load(os.path.join(OUT, "rays_small.npz"))
+        gen_loss(fixture_id_module(), *(torch.from_numpy(g[k]) for k in ("ori", "dirs", "rgb")))
         sys.exit(0)
     if "--only-heavy" in sys.argv:  # add the heavy-tail fixture without touching the others
         gen_rays()
@@ -263,5 +311,6 @@ if __name__ == "__main__":
     gen_id_module_peaked(ori, dirs, rgb)
     gen_line_intersection()
     gen_pose(idm, ori, dirs, rgb)
+    gen_loss(idm, ori, dirs, rgb)
     gen_ply()
     os.system(f"du -sh {OUT}")
