@@ -390,3 +390,124 @@ def test_c_abi_argument_validation_needs_no_gpu(sx):
     # empty inputs are not errors
     assert lib.sixdgs_degrade_mask(P, 0, 50, P, None, None) == 0 and lib.sixdgs_raygen_cells(P, None, 0, 50, P, None) == 0
     assert lib.sixdgs_version() >= 200
+
+
+def test_cfg_args_parser_and_experiment_discovery(tmp_path):
+    """our replacement of the reference's ANTLR cfg_args grammar (cfg_grammar/Namespace.g4: INT, FLOAT, BOOL, STRING) on
+    the reference's own example (parse_config.py:46) and on what argparse really writes; directory-of-experiments
+    discovery with the reference's naming rules (file_utils.py:19-77)"""
+    import importlib
+    drv = importlib.import_module("6dgs_b200.eval_driver")
+    cfg = drv.parse_config("Namespace(sh_degree=3, source_path='/home/mbortolon/data/datasets/360_v2/bicycle', "
+                           "model_path='./output/ec0d365d-5', images='images', resolution=-1, white_background=False, "
+                           "data_device='cuda', eval=True)")
+    assert cfg == {"sh_degree": 3, "source_path": "/home/mbortolon/data/datasets/360_v2/bicycle",
+                   "model_path": "./output/ec0d365d-5", "images": "images", "resolution": -1, "white_background": False,
+                   "data_device": "cuda", "eval": True}
+    assert drv.parse_config('Namespace(a=1.5, b=None, c=[1, 2], d=true, e="x y", f=+3, g=-0.25)') == \
+        {"a": 1.5, "b": None, "c": [1, 2], "d": True, "e": "x y", "f": 3, "g": -0.25}
+    assert drv.parse_config(" Namespace()\n") == {}
+    for bad in ("Foo(a=1)", "Namespace(a=b)", "Namespace(1)", "Namespace(a=1", "Namespace(a=__import__('os'))", "Namespace(**x)"):
+        with pytest.raises(ValueError):
+            drv.parse_config(bad)
+    root = tmp_path / "exps"
+    for name, its in (("synthetic_lego_7", (7000, 30000)), ("synthetic_hot_dog_12", (30000,)), ("synthetic_empty_3", ()),
+                      ("mip_360_bicycle_1", (100,)), ("synthetic_lego_9", ("junk", 500))):
+        for it in its:
+            d = root / name / "point_cloud" / f"iteration_{it}"
+            d.mkdir(parents=True)
+            (d / "point_cloud.ply").write_bytes(b"ply")
+        (root / name).mkdir(parents=True, exist_ok=True)
+    (root / "synthetic_lego_7" / "point_cloud" / "iteration_40000").mkdir()  # a checkpoint directory without its PLY
+    (root / "synthetic_file_1").write_text("not a directory")
+    (root / "synthetic_lego_7" / "cfg_args").write_text("Namespace(sh_degree=2, fps_sampling=None, source_path='/d/lego')")
+    objs = drv.parse_exp_dir(str(root), "synthetic_")
+    assert list(objs) == ["3"] * 0 + ["12", "7", "9"]  # sorted directory order; the object without a checkpoint is skipped
+    assert objs["12"]["category_name"] == "synthetic_hot_dog" and objs["7"]["category_name"] == "synthetic_lego"
+    assert objs["7"]["checkpoint_filepath"].endswith("synthetic_lego_7/point_cloud/iteration_30000/point_cloud.ply")
+    assert objs["9"]["checkpoint_filepath"].endswith("iteration_500/point_cloud.ply")
+    assert list(drv.parse_exp_dir(str(root), "mip_360_")) == ["1"] and len(drv.parse_exp_dir(str(root), "")) == 4
+    assert drv.get_highest_valid_checkpoint(str(root / "synthetic_empty_3")) == ""
+    a = drv.get_checkpoint_arguments(str(root / "synthetic_lego_7"))
+    assert a.sh_degree == 2 and a.fps_sampling is None and a.source_path == "/d/lego" and a.not_there is None
+
+
+class _StandInPackage:
+    """what eval_driver.main needs from the package, without a GPU: records the calls, returns canned results"""
+
+    def __init__(self, synthetic, stored_degree=3, fail_on=()):
+        import types
+        self.calls, self.synthetic, self.fail_on = [], synthetic, fail_on
+        outer = self
+
+        class Scene:
+            max_sh_degree = stored_degree
+
+            @classmethod
+            def load_ply(cls, path, device="cuda"):
+                outer.calls.append(("load_ply", path, str(device)))
+                if any(f in path for f in outer.fail_on):
+                    raise RuntimeError("corrupt checkpoint")
+                return cls()
+
+        class Idm(torch.nn.Module):
+            def __init__(self, backbone_type, score_impl=None, backbone=None):
+                super().__init__()
+                outer.calls.append(("idm", backbone_type, score_impl, type(backbone).__name__))
+
+        self.GaussianScene, self.IdentificationModule = Scene, Idm
+        self.DistanceBasedScoreLoss = lambda: "loss_fn"
+        self.generate_all_possible_rays = lambda scene, sample_quadricell_targets=50, max_ellipsoids=1000: (
+            outer.calls.append(("rays", sample_quadricell_targets, max_ellipsoids)) or tuple(torch.zeros(17, 3) for _ in range(3)))
+
+        def tpe(cams, idm, ori, dirs, rgb, model_up, sequence_id="", category_id="", loss_fn=None):
+            outer.calls.append(("tpe", len(cams), sequence_id, category_id, loss_fn, tuple(round(float(x), 4) for x in model_up)))
+            res = [{"frame_id": i, "sequence_id": sequence_id, "pred_c2w": torch.eye(4).tolist(), "gt_c2w": torch.eye(4).tolist()}
+                   for i in range(len(cams))]
+            return res, 0.25, 3.0, (0.5 if loss_fn else -1.0), (0.75 if loss_fn else -1.0)
+
+        self.test_pose_estimation = tpe
+        del types
+
+
+def test_eval_driver_control_flow_single_and_directory_modes(synthetic, tmp_path):
+    """eval_driver.main with a stand-in for the package (the real one needs a GPU; tests/test_gpu_pipeline.py runs it):
+    single experiment with --oracle_rays, cfg_args / PLY degree mismatch, and the reference driver's
+    directory-of-experiments mode with a failing object"""
+    import importlib
+    import json
+    import shutil
+    drv = importlib.import_module("6dgs_b200.eval_driver")
+    exp, img_dir, p = _write_experiment(tmp_path, synthetic)
+    (exp / "cfg_args").write_text("Namespace(sh_degree=3, source_path='/data/x', white_background=False)")
+    pk = _StandInPackage(synthetic)
+    out = tmp_path / "r.json"
+    res = drv.main(["--exp_path", str(exp), "--images", str(img_dir), "--out", str(out), "--every", "2", "--oracle_rays",
+                    "--device", "cpu", "--max_ellipsoids", "0", "--backbone", "synthetic"], sx=pk)
+    assert json.load(open(out)) == json.loads(json.dumps(res))
+    assert res["n_rays"] == 17 and res["trained_weights"] is True and res["source_path"] == "/data/x"
+    assert res["oracle_rays"] == {"avg_translation_error": 0.25, "avg_angular_error": 3.0, "avg_score_loss": 0.5, "recall": 0.75}
+    kinds = [c[0] for c in pk.calls]
+    assert kinds == ["load_ply", "idm", "rays", "tpe", "tpe"] and pk.calls[2] == ("rays", 50, None)
+    assert pk.calls[1] == ("idm", "dino", "tc_f16x2", "SyntheticBackbone") and pk.calls[0][2] == "cpu"
+    up = np.mean([p["R"][i].numpy()[:3, 1] for i in range(3)], axis=0)
+    assert pk.calls[3][1:5] == (2, "exp", "", "loss_fn") and pk.calls[4][4] is None  # every 2nd of 3 cameras; oracle pass first
+    np.testing.assert_allclose(pk.calls[4][5], up, atol=1e-4)  # model up from ALL cameras
+    with pytest.raises(ValueError, match="sh_degree"):
+        drv.main(["--exp_path", str(exp), "--images", str(img_dir), "--out", str(out), "--device", "cpu"],
+                 sx=_StandInPackage(synthetic, stored_degree=2))
+    # directory of experiments: two blender objects (one of them fails to load), one of another dataset
+    root = tmp_path / "all"
+    for name in ("synthetic_lego_7", "synthetic_chair_8", "tt_truck_1"):
+        shutil.copytree(exp, root / name)
+    shutil.copytree(img_dir, tmp_path / "imgs" / "synthetic_lego_7")
+    shutil.copytree(img_dir, tmp_path / "imgs" / "synthetic_chair_8")
+    pk = _StandInPackage(synthetic, fail_on=("synthetic_chair_8",))
+    res = drv.main(["--exp_path", str(root), "--data_type", "blender", "--images", str(tmp_path / "imgs"), "--out", str(out),
+                    "--every", "1", "--device", "cpu"], sx=pk)
+    assert list(res["objects"]) == ["7"] and len(res["results"]) == 3 and res["results"][0]["sequence_id"] == "7"
+    assert [c for c in pk.calls if c[0] == "tpe"][0][2:4] == ("7", "synthetic_lego")
+    assert sum(c[0] == "load_ply" for c in pk.calls) == 2 and pk.calls[0][1].endswith("synthetic_chair_8/point_cloud/iteration_30000/point_cloud.ply")
+    assert "results" not in res["objects"]["7"] and res["objects"]["7"]["n_rays"] == 17
+    with pytest.raises(FileNotFoundError):
+        drv.main(["--exp_path", str(root), "--data_type", "mip360", "--out", str(out), "--device", "cpu"], sx=pk)
