@@ -28,7 +28,7 @@ from typing import Optional
 
 import torch
 
-from . import ops
+from . import ops, train_ops
 from ._lib import BF16, F16F8, F16X2, F32, SixdgsError
 from .camera_up import CameraDirectionPredictor
 from .image_tokens import BackboneWrapper
@@ -280,16 +280,17 @@ class IdentificationModule(torch.nn.Module):
             raise _lib.SixdgsError("rays must be CUDA tensors (this package has no CPU path)")
         lin = torch.nn.functional.linear
         tok_pe, tok, grid = self.backbone_wrapper(img, mask)
-
-        def pe(p, nf):
-            ang = (p[..., None] * (2.0 ** torch.arange(nf, device=p.device, dtype=p.dtype))).reshape(p.shape[0], -1)
-            return torch.cat((torch.sin(ang), torch.cos(ang)), -1)
-
         rp = self.ray_preprocessor
-        x = torch.cat((rays_ori, rays_dir, rays_rgb, pe(rays_ori, rp.pospe), pe(rays_dir, rp.viewpe), pe(rays_rgb, rp.rgbpe)), -1)
-        fea = rp.mlp2(torch.cat((rp.mlp(x), x), -1))
-        q = lin(tok_pe, self.attention.q_proj.weight, self.attention.q_proj.bias)
-        k = lin(fea, self.attention.k_proj.weight, self.attention.k_proj.bias)
+        if os.environ.get("SIXDGS_TRAIN_MLP", "torch") == "kernels":
+            # every GEMM of the ray MLP and of the two projections, forward and backward, on sixdgs_linear
+            # (train_ops._LinearFunction); torch keeps the PE, the concat, the ReLU masks and the bias sums
+            k = train_ops.ray_keys(rp, self.attention, rays_ori, rays_dir, rays_rgb)
+            q = train_ops.image_queries(self.attention, tok_pe)
+        else:
+            x = train_ops.ray_mlp_input(rp, rays_ori, rays_dir, rays_rgb)
+            fea = rp.mlp2(torch.cat((rp.mlp(x), x), -1))
+            q = lin(tok_pe, self.attention.q_proj.weight, self.attention.q_proj.bias)
+            k = lin(fea, self.attention.k_proj.weight, self.attention.k_proj.bias)
         if os.environ.get("SIXDGS_TRAIN_SCORE", "kernels") == "torch":  # pure torch-op route (kept as the cross-check)
             amap = torch.softmax((q @ k.t()) / (q.shape[-1] ** 0.5), dim=-1)
             return amap.sum(0), amap, tok, self._camera_up(grid)
