@@ -449,8 +449,35 @@ def trace(msg):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def arm_watchdog():
+    """A bench that cannot finish (a wedged collective, a kernel that never retires) must end on its own with a
+    diagnostic instead of holding the GPU box until somebody else's limit kills it: after SIXDGS_BENCH_WATCHDOG_S
+    seconds (default 1500; the default run takes about a minute; 0 disables) the process prints where it was and
+    exits 124.  A daemon timer: it costs nothing on the normal path and dies with the process."""
+    import threading
+
+    limit = float(os.environ.get("SIXDGS_BENCH_WATCHDOG_S", "1500"))
+    if limit <= 0:
+        return None
+
+    def fire():
+        import faulthandler
+
+        sys.stderr.write(f"[bench] watchdog: no result after {limit:.0f} s on rank {os.environ.get('RANK', '0')}; "
+                         "stacks follow, exiting 124\n")
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        sys.stderr.flush()
+        os._exit(124)
+
+    t = threading.Timer(limit, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     args = parse()
+    arm_watchdog()
     if args.impl == "reference":
         run_reference_arm(args)
         return
