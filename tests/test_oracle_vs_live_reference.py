@@ -137,3 +137,68 @@ def test_line_intersection_and_pose_helpers(ref, oracle, seed):
     assert torch.equal(oracle.exclude_negatives(centre, o, d), li.exclude_negatives(centre, o, d))
     fwd, up = torch.randn(3, generator=g), torch.randn(3, generator=g)
     torch.testing.assert_close(oracle.make_rotation_mat(fwd, up), li.make_rotation_mat(fwd, up), rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The PACKAGE's boundary code that is plain torch (it runs on the CPU): image front end, camera-up head, loss
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,masked", [((64, 64), False), ((300, 500), True), ((1080, 1920), True), ((500, 300), False)])
+def test_package_image_front_end_vs_reference(ref, sx, synthetic, shape, masked):
+    """a9 (backbone.py:82-139): resize 256 / crop 224 / normalise / mask -> 16x16 -> boolean compaction, on square,
+    landscape and portrait images, with and without a partial mask"""
+    bb_ref = importlib.import_module("pose_estimation.backbone").BackboneWrapper(backbone_type="dino").eval()
+    bb = sx.BackboneWrapper("dino", backbone=synthetic.SyntheticBackbone()).eval()
+    g = torch.Generator().manual_seed(shape[0] + shape[1])
+    img = torch.rand(*shape, 3, generator=g)
+    mask = torch.ones(shape, dtype=torch.bool)
+    if masked:  # an off-centre ellipse of foreground, like an object mask
+        yy, xx = torch.meshgrid(torch.linspace(-1, 1, shape[0]), torch.linspace(-1, 1, shape[1]), indexing="ij")
+        mask = ((yy - 0.1) / 0.7) ** 2 + ((xx + 0.15) / 0.5) ** 2 < 1.0
+    with torch.no_grad():
+        tok_pe_r, tok_r, grid_r = bb_ref(img, mask)
+        tok_pe, tok, grid = bb(img, mask)
+    assert tok_pe.shape == tok_pe_r.shape and (tok_pe.shape[0] < 256) == masked
+    torch.testing.assert_close(tok_pe, tok_pe_r, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(tok, tok_r, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(grid, grid_r.reshape(grid.shape), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("seed", SEEDS[:2])
+def test_package_camera_up_head_vs_reference(ref, sx, synthetic, seed):
+    """a15 (camera_direction_network.py:81-89, identification_module.py:87-90): the im2col + GEMM head of the package
+    against the reference's Conv2d head with the same weights"""
+    w = synthetic.synth_id_weights(seed=seed)
+    idm_ref = ref["identification_module"].IdentificationModule(backbone_type="dino").eval()
+    idm_ref.load_state_dict(w, strict=False)
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone()).eval()
+    idm.load_state_dict(w, strict=False)
+    grid = torch.randn(384, 16, 16, generator=torch.Generator().manual_seed(seed))
+    with torch.no_grad():
+        up_ref = torch.nn.functional.normalize(idm_ref.camera_direction_prediction_network(grid), dim=-1)
+        up = idm._camera_up(grid)
+    torch.testing.assert_close(up, up_ref.reshape(up.shape), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_package_score_loss_vs_reference(ref, sx, seed):
+    """distance_based_loss.py:5-283 on fresh poses, intrinsics and rays (landscape and square observation shapes)"""
+    dbl = importlib.import_module("pose_estimation.distance_based_loss")
+    g = torch.Generator().manual_seed(seed)
+    n = 3000
+    ori = torch.randn(n, 3, generator=g)
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    pred = torch.rand(n, generator=g) * 0.2
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    pose = torch.eye(4)
+    pose[:3, :3], pose[:3, 3] = q * torch.sign(torch.linalg.det(q)), torch.randn(3, generator=g) * 2.5
+    K = torch.tensor([[700.0, 0.0, 400.0], [0.0, 690.0, 300.0], [0.0, 0.0, 1.0]])
+    for shape in ((800, 800), (600, 800)):
+        _, ins_r, t_r, td_r = dbl.best_one_to_one_rays_selector(K, pose, shape, dirs, ori, backbone_wh=(16, 16))
+        _, ins, t, td = sx.best_one_to_one_rays_selector(K, pose, shape, dirs, ori, backbone_wh=(16, 16))
+        assert (ins != ins_r).sum() <= 1  # a projection within 1 ulp of a patch-grid edge may land on the other side
+        torch.testing.assert_close(t, t_r, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(td, td_r, rtol=1e-5, atol=1e-6)
+    loss_r, target_r = dbl.DistanceBasedScoreLoss()(pred, pose, K, ori, dirs, 256, (16, 16), model_up=None)
+    loss, target = sx.DistanceBasedScoreLoss()(pred, pose, K, ori, dirs, 256, (16, 16), model_up=None)
+    torch.testing.assert_close(target, target_r, rtol=1e-5, atol=1e-6)
+    assert abs(float(loss) - float(loss_r)) <= 1e-5 * abs(float(loss_r))
