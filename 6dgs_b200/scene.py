@@ -91,6 +91,19 @@ class GaussianScene:
     def get_rotation(self):
         return torch.nn.functional.normalize(self._rotation)
 
+    def get_rotation_mat(self):
+        """[N,3,3] rotation of every Gaussian (reference gaussian_model.py:133-134 -> general_utils.py:103-126): the
+        stored quaternion (w,x,y,z) is normalised by ``get_rotation`` and once more by the matrix builder, in that
+        order -- the ray-generation kernel does the same two normalisations in registers (csrc/raygen.cu) and never
+        calls this; it is here for callers of the reference getter."""
+        q = self.get_rotation
+        q = q / torch.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2] + q[:, 3] * q[:, 3])[:, None]
+        w, x, y, z = q.unbind(-1)
+        rows = (1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y))
+        return torch.stack(rows, dim=-1).reshape(-1, 3, 3)
+
     @property
     def get_features(self):
         return self._features

@@ -202,3 +202,18 @@ def test_package_score_loss_vs_reference(ref, sx, seed):
     loss, target = sx.DistanceBasedScoreLoss()(pred, pose, K, ori, dirs, 256, (16, 16), model_up=None)
     torch.testing.assert_close(target, target_r, rtol=1e-5, atol=1e-6)
     assert abs(float(loss) - float(loss_r)) <= 1e-5 * abs(float(loss_r))
+
+
+@pytest.mark.parametrize("seed", SEEDS[:2])
+def test_package_scene_getters_vs_reference_model(ref, sx, synthetic, oracle, seed):
+    """a1 (gaussian_model.py:125-158, general_utils.py:103-126): the getters the hot path reads, bit for bit, from a
+    scene adopted from the reference's own GaussianModel"""
+    sc = synthetic.synth_scene(300, seed=seed)
+    gm = ref["shims"].make_gaussian_model(sc["xyz"], sc["scaling"], sc["rotation"], sc["features_dc"],
+                                          sc["features_rest"], sc["sh_degree"])
+    scene = sx.GaussianScene.from_gaussian_model(gm, device="cpu")
+    assert scene.active_sh_degree == gm.active_sh_degree == scene.max_sh_degree == 3
+    assert torch.equal(scene.get_xyz, gm.get_xyz) and torch.equal(scene.get_scaling, gm.get_scaling)
+    assert torch.equal(scene.get_rotation, gm.get_rotation) and torch.equal(scene.get_features, gm.get_features)
+    assert torch.equal(scene.get_rotation_mat(), gm.get_rotation_mat())
+    assert torch.equal(oracle.quat_to_rotmat(sc["rotation"]), gm.get_rotation_mat())
