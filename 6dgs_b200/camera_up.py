@@ -13,8 +13,13 @@ def _reducer(channels: int, kernel: int, count: int) -> torch.nn.Sequential:
 
 
 class CameraDirectionPredictor(torch.nn.Module):
-    def __init__(self, image_feature_channel: int = 384, image_size=(16, 16), featureC: int = 256, fea_output: int = 3):
+    def __init__(self, image_feature_channel: int = 256, image_size=(16, 16), pospe: int = 8, featureC: int = 256,
+                 fea_output: int = 3):
+        """same positional order and defaults as the reference (camera_direction_network.py:8-15); ``pospe`` only
+        sets two attributes there (``direction_input``, ``pospe``) that no forward path reads"""
         super().__init__()
+        self.pospe = pospe
+        self.direction_input = 2 * pospe * 3 + 3
         self.dim_reducer1 = _reducer(image_feature_channel, 5, 3)
         self.dim_reducer2 = _reducer(image_feature_channel, 4, 1)
         side = [s - 3 * 4 - 3 for s in image_size]

@@ -37,11 +37,14 @@ from .image_tokens import BackboneWrapper
 class RayPreprocessor(torch.nn.Module):
     """Parameter container + kernel call for the ray MLP (reference ray_preprocessor.py:11-46)."""
 
-    def __init__(self, viewpe: int = 8, pospe: int = 8, rgbpe: int = 6, featureC: int = 512, fea_output: int = 384):
+    def __init__(self, viewpe: int = 8, pospe: int = 8, rgbpe: int = 6, featureC: int = 128, fea_output: int = 128):
+        """signature and defaults of the reference (ray_preprocessor.py:12-19).  The kernels are specialised for the one
+        configuration the reference ever builds (identification_module.py:16-18: width 512, output 384), so the
+        reference's own defaults (128, 128) are refused rather than silently widened."""
         super().__init__()
         if (viewpe, pospe, rgbpe, featureC, fea_output) != (8, 8, 6, 512, 384):
-            raise NotImplementedError("the kernels are specialised for the reference configuration "
-                                      "(PE 8/8/6, width 512, output 384; identification_module.py:16-18)")
+            raise NotImplementedError("the kernels are specialised for the configuration IdentificationModule builds "
+                                      "(PE 8/8/6, featureC=512, fea_output=384; identification_module.py:16-18)")
         self.in_mlpC = 2 * viewpe * 3 + 3 + 2 * pospe * 3 + 3 + 2 * rgbpe * 3 + 3
         relu = lambda: torch.nn.ReLU(inplace=True)  # noqa: E731
         self.mlp = torch.nn.Sequential(torch.nn.Linear(self.in_mlpC, featureC), relu(),

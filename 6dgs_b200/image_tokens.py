@@ -133,8 +133,9 @@ class BackboneWrapper(torch.nn.Module):
             transforms.Resize(self.backbone_wh[0], interpolation=bilinear, antialias=True)])
 
     @staticmethod
-    def get_img_position_encoding(shape, freqs, dtype=torch.float32, device="cpu"):
+    def get_img_position_encoding(img_features_shape, freqs, dtype=torch.float32, device="cpu"):
         """[x, y, sin(x*2^f) sin(y*2^f) (coordinate-major), cos(...)] on linspace(-1,1) (backbone.py:116-139)."""
+        shape = tuple(img_features_shape)
         axes = [torch.linspace(-1.0, 1.0, steps=s, dtype=dtype, device=device) for s in shape]
         pos = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, len(shape))
         bands = 2.0 ** torch.arange(freqs, dtype=dtype, device=pos.device)

@@ -217,3 +217,65 @@ def test_package_scene_getters_vs_reference_model(ref, sx, synthetic, oracle, se
     assert torch.equal(scene.get_rotation, gm.get_rotation) and torch.equal(scene.get_features, gm.get_features)
     assert torch.equal(scene.get_rotation_mat(), gm.get_rotation_mat())
     assert torch.equal(oracle.quat_to_rotmat(sc["rotation"]), gm.get_rotation_mat())
+
+
+def test_package_signatures_are_the_reference_signatures(ref, sx):
+    """every mirrored callable takes the reference's parameters, in the reference's order, with the
+    reference's defaults (package-only parameters may follow them)."""
+    import inspect
+
+    def R(mod):
+        return importlib.import_module("pose_estimation." + mod)
+
+    idm_r, idm = R("identification_module").IdentificationModule, sx.IdentificationModule
+    bw_r, bw = R("backbone").BackboneWrapper, sx.BackboneWrapper
+    loss_r = R("distance_based_loss")
+    pairs = {
+        "generate_all_possible_rays": (R("sampling").generate_all_possible_rays, sx.generate_all_possible_rays),
+        "IdentificationModule.__init__": (idm_r.__init__, idm.__init__),
+        "IdentificationModule.forward": (idm_r.forward, idm.forward),
+        "IdentificationModule.run_attention": (idm_r.run_attention, idm.run_attention),
+        "IdentificationModule.test_image": (idm_r.test_image, idm.test_image),
+        "compute_line_intersection_impl2": (R("line_intersection").compute_line_intersection_impl2,
+                                            sx.compute_line_intersection_impl2),
+        "exclude_negatives": (R("line_intersection").exclude_negatives, sx.exclude_negatives),
+        "make_rotation_mat": (R("line_intersection").make_rotation_mat, sx.make_rotation_mat),
+        "sym_eig_3x3": (R("sym_eig_3x3").sym_eig_3x3, importlib.import_module("6dgs_b200.eig3").sym_eig_3x3),
+        "test_pose_estimation": (R("test").test_pose_estimation, sx.test_pose_estimation),
+        "RayPreprocessor.__init__": (R("ray_preprocessor").RayPreprocessor.__init__, sx.RayPreprocessor.__init__),
+        "RayPreprocessor.forward": (R("ray_preprocessor").RayPreprocessor.forward, sx.RayPreprocessor.forward),
+        "MultiHeadAttention.__init__": (R("our_multihead_attention").MultiHeadAttention.__init__, sx.MultiHeadAttention.__init__),
+        "MultiHeadAttention.forward": (R("our_multihead_attention").MultiHeadAttention.forward, sx.MultiHeadAttention.forward),
+        "BackboneWrapper.__init__": (bw_r.__init__, bw.__init__),
+        "BackboneWrapper.forward": (bw_r.forward, bw.forward),
+        "BackboneWrapper.get_img_position_encoding": (bw_r.get_img_position_encoding, bw.get_img_position_encoding),
+        "CameraDirectionPredictor.__init__": (R("camera_direction_network").CameraDirectionPredictor.__init__,
+                                              sx.CameraDirectionPredictor.__init__),
+        "CameraDirectionPredictor.forward": (R("camera_direction_network").CameraDirectionPredictor.forward,
+                                             sx.CameraDirectionPredictor.forward),
+        "DistanceBasedScoreLoss.__init__": (loss_r.DistanceBasedScoreLoss.__init__, sx.DistanceBasedScoreLoss.__init__),
+        "DistanceBasedScoreLoss.forward": (loss_r.DistanceBasedScoreLoss.forward, sx.DistanceBasedScoreLoss.forward),
+        "best_one_to_one_rays_selector": (loss_r.best_one_to_one_rays_selector, sx.best_one_to_one_rays_selector),
+        "GaussianModel.get_rotation_mat": (importlib.import_module("scene.gaussian_model").GaussianModel.get_rotation_mat,
+                                           sx.GaussianScene.get_rotation_mat),
+    }
+    # the one intended difference: the enum default OutputAugmentationTypes.NONE is accepted as None / "NONE" / the enum
+    allowed = {("IdentificationModule.__init__", "camera_up_output_augmentation")}
+    problems = []
+    for name, (f_ref, f_pkg) in pairs.items():
+        p_ref = list(inspect.signature(f_ref).parameters.values())
+        p_pkg = list(inspect.signature(f_pkg).parameters.values())
+        for i, p in enumerate(p_ref):
+            if i >= len(p_pkg) or p_pkg[i].name != p.name:
+                problems.append(f"{name}: parameter {i} is {p.name!r} upstream, "
+                                f"{p_pkg[i].name if i < len(p_pkg) else None!r} here")
+            elif p.default is not inspect.Parameter.empty and repr(p_pkg[i].default) != repr(p.default) \
+                    and (name, p.name) not in allowed:
+                problems.append(f"{name}: default of {p.name!r} is {p.default!r} upstream, {p_pkg[i].default!r} here")
+    assert not problems, "\n".join(problems)
+    # the reference's own default widths are refused loudly, not silently replaced by the supported ones
+    with pytest.raises(NotImplementedError):
+        sx.RayPreprocessor()
+    idm_obj = sx.IdentificationModule("dino", R("identification_module").OutputAugmentationTypes.NONE,
+                                      backbone=importlib.import_module("6dgs_b200.synthetic").SyntheticBackbone())
+    assert idm_obj.camera_direction_prediction_network.pospe == 8
