@@ -137,6 +137,12 @@ def test_line_intersection_and_pose_helpers(ref, oracle, seed):
     assert torch.equal(oracle.exclude_negatives(centre, o, d), li.exclude_negatives(centre, o, d))
     fwd, up = torch.randn(3, generator=g), torch.randn(3, generator=g)
     torch.testing.assert_close(oracle.make_rotation_mat(fwd, up), li.make_rotation_mat(fwd, up), rtol=1e-6, atol=1e-7)
+    # the package's two helpers that are plain tensor algebra (pose_solve.py) run on the CPU as well
+    pkg = importlib.import_module("6dgs_b200.pose_solve")
+    assert torch.equal(pkg.exclude_negatives(centre, o, d), li.exclude_negatives(centre, o, d))
+    rot = pkg.make_rotation_mat(fwd, up)
+    assert rot.device.type == "cpu"  # upstream returns a CPU tensor whatever the inputs' device
+    torch.testing.assert_close(rot, li.make_rotation_mat(fwd, up), rtol=1e-6, atol=1e-7)
 
 
 # ------------------------------------------------------------------------------------------------------------------
