@@ -44,7 +44,10 @@ def find_point_cloud(exp_path: str) -> str:
     """the ``point_cloud/iteration_<N>/point_cloud.ply`` with the largest N; directory names whose second ``_`` component
     is not an integer, and checkpoint directories without their PLY, are ignored (reference file_utils.py:19-43)"""
     best, best_path = None, ""
-    for path in glob.glob(os.path.join(exp_path, "point_cloud", "iteration_*", "point_cloud.ply")):
+    # upstream walks the directory names in reverse lexicographic order and lets a later equal iteration number win
+    # ("iteration_7000" before "iteration_07000"): same walk here, so ties resolve identically
+    for path in sorted(glob.glob(os.path.join(exp_path, "point_cloud", "iteration_*", "point_cloud.ply")),
+                       key=lambda p: os.path.basename(os.path.dirname(p)), reverse=True):
         parts = os.path.basename(os.path.dirname(path)).split("_")
         try:
             it = int(parts[1])

@@ -285,3 +285,40 @@ def test_package_signatures_are_the_reference_signatures(ref, sx):
     idm_obj = sx.IdentificationModule("dino", R("identification_module").OutputAugmentationTypes.NONE,
                                       backbone=importlib.import_module("6dgs_b200.synthetic").SyntheticBackbone())
     assert idm_obj.camera_direction_prediction_network.pospe == 8
+
+
+def test_package_experiment_discovery_vs_reference_file_utils(ref, tmp_path, monkeypatch):
+    """pose_estimation/file_utils.py:19-72 (checkpoint choice, directory-of-experiments naming) run live.  Its module
+    imports the ANTLR grammar, which no longer deserialises here, so ``cfg_grammar`` is stubbed for the import only --
+    the two functions compared do not touch it."""
+    import types
+    stub = types.ModuleType("cfg_grammar")
+    stub.parse_config = lambda text: {}
+    monkeypatch.setitem(sys.modules, "cfg_grammar", stub)
+    sys.modules.pop("pose_estimation.file_utils", None)
+    fu = importlib.import_module("pose_estimation.file_utils")
+    drv = importlib.import_module("6dgs_b200.eval_driver")
+    root = tmp_path / "exps"
+    layout = {
+        "synthetic_chair_001": ["iteration_7000", "iteration_30000", "iteration_best", "iteration_07000"],
+        "synthetic_lego_car_17": ["iteration_500", "iteration_0500"],
+        "synthetic_empty_3": [],                       # no checkpoint: skipped with a message
+        "synthetic_noply_4": ["iteration_100:noply"],  # directory without its PLY
+        "mip_360_garden_9": ["iteration_10"],          # another dataset's prefix
+        "synthetic_dup_17": ["iteration_1"],           # same sequence id as lego_car_17: the later directory wins
+    }
+    for exp, its in layout.items():
+        (root / exp / "point_cloud").mkdir(parents=True)
+        for it in its:
+            name, _, flag = it.partition(":")
+            (root / exp / "point_cloud" / name).mkdir()
+            if flag != "noply":
+                (root / exp / "point_cloud" / name / "point_cloud.ply").write_bytes(b"ply\n")
+    (root / "synthetic_file_5").write_text("not a directory")
+    for exp in layout:
+        assert drv.get_highest_valid_checkpoint(str(root / exp)) == fu.get_highest_valid_checkpoint(str(root / exp)), exp
+    for prefix in ("synthetic_", "mip_360_", "", "tt_"):
+        assert drv.parse_exp_dir(str(root), prefix) == fu.parse_exp_dir(str(root), prefix), prefix
+    d_ref, d_pkg = fu.dotdict({"a": 1}), drv.dotdict({"a": 1})
+    assert d_pkg.a == d_ref.a == 1 and d_pkg.missing is None and d_ref.missing is None
+    sys.modules.pop("pose_estimation.file_utils", None)
