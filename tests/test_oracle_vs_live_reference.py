@@ -322,3 +322,21 @@ def test_package_experiment_discovery_vs_reference_file_utils(ref, tmp_path, mon
     d_ref, d_pkg = fu.dotdict({"a": 1}), drv.dotdict({"a": 1})
     assert d_pkg.a == d_ref.a == 1 and d_pkg.missing is None and d_ref.missing is None
     sys.modules.pop("pose_estimation.file_utils", None)
+
+
+def test_package_loads_a_state_dict_saved_by_the_reference_module(ref, sx, synthetic):
+    """id_module.th is ``IdentificationModule.state_dict()`` of the reference (train.py:309-317): every key outside the
+    third-party backbone must exist here with the same shape, and loading it must leave nothing unexpected"""
+    idm_ref = ref["identification_module"].IdentificationModule(backbone_type="dino")
+    sd = idm_ref.state_dict()
+    idm = sx.IdentificationModule("dino", backbone=synthetic.SyntheticBackbone())
+    own = idm.state_dict()
+    hot = [k for k in sd if not k.startswith("backbone_wrapper.image_preprocessing_net.")]
+    assert len(hot) >= 24
+    for k in hot:
+        assert k in own and own[k].shape == sd[k].shape, k
+    res = idm.load_state_dict(sd, strict=False)
+    assert not [k for k in res.unexpected_keys if not k.startswith("backbone_wrapper.image_preprocessing_net.")]
+    assert not [k for k in res.missing_keys if not k.startswith("backbone_wrapper.image_preprocessing_net.")]
+    for k in hot:
+        assert torch.equal(idm.state_dict()[k], sd[k]), k
