@@ -511,3 +511,36 @@ def test_eval_driver_control_flow_single_and_directory_modes(synthetic, tmp_path
     assert "results" not in res["objects"]["7"] and res["objects"]["7"]["n_rays"] == 17
     with pytest.raises(FileNotFoundError):
         drv.main(["--exp_path", str(root), "--data_type", "mip360", "--out", str(out), "--device", "cpu"], sx=pk)
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """every prototype of include/sixdgs.h against the argument / return types the ctypes binding (6dgs_b200/_lib.py)
+    attaches: pointer -> c_void_p, int64_t -> c_int64, size_t -> c_size_t, float / double / int by value.  A drift here
+    would pass garbage on the stack without any compiler noticing."""
+    import ctypes
+    import importlib
+    import re
+    lib = importlib.import_module("6dgs_b200._lib")
+    src = open(os.path.join(ROOT, "include", "sixdgs.h")).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", " ", src)
+    protos = re.findall(r"\b(int|size_t|const char\s*\*)\s+(sixdgs_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert {p[1] for p in protos} == set(lib._SIGNATURES) and len(protos) >= 40
+
+    def kind(arg):
+        a = " ".join(arg.split())
+        if a in ("void", ""):
+            return None
+        if "*" in a:
+            return ctypes.c_void_p
+        for pat, t in ((r"\bint64_t\b", ctypes.c_int64), (r"\bsize_t\b", ctypes.c_size_t), (r"\bdouble\b", ctypes.c_double),
+                       (r"\bfloat\b", ctypes.c_float), (r"\bint\b", ctypes.c_int)):
+            if re.search(pat, a):
+                return t
+        raise AssertionError(f"unrecognised parameter {a!r}")
+
+    for ret, name, args in protos:
+        want = [k for k in (kind(a) for a in args.split(",")) if k is not None]
+        got, res = lib._SIGNATURES[name]
+        assert want == got, (name, [k.__name__ for k in want], [k.__name__ for k in got])
+        assert res == {"int": ctypes.c_int, "size_t": ctypes.c_size_t}.get(ret, ctypes.c_char_p), name
