@@ -84,6 +84,7 @@ class _LinearFunction(torch.autograd.Function):
     def forward(ctx, x, w, b, relu: bool):
         y = gemm_nt(x, w, b, relu)
         ctx.relu = bool(relu)
+        ctx.dtypes = (x.dtype, w.dtype, b.dtype if b is not None else None)  # gradients go back in the inputs' dtypes
         ctx.save_for_backward(x.detach(), w.detach(), y if relu else None)
         return y
 
@@ -96,11 +97,11 @@ class _LinearFunction(torch.autograd.Function):
         gy = gy.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm_nt(gy, w.t())          # [m, n] x [k, n]^T
+            gx = gemm_nt(gy, w.t()).to(ctx.dtypes[0])          # [m, n] x [k, n]^T
         if ctx.needs_input_grad[1]:
-            gw = gemm_tn(gy, x)              # [n, k]
+            gw = gemm_tn(gy, x).to(ctx.dtypes[1])              # [n, k]
         if ctx.needs_input_grad[2]:
-            gb = gy.sum(0)
+            gb = gy.sum(0).to(ctx.dtypes[2])
         return gx, gw, gb, None
 
 

@@ -135,3 +135,15 @@ def test_no_rays(train_ops):
     assert y.shape == (0, 384)
     y.sum().backward()
     assert w.grad.abs().sum() == 0 and not train_ops._calls
+
+
+def test_gradients_come_back_in_the_inputs_dtype(train_ops):
+    """the kernel computes in fp32; a double-precision parameter (e.g. a module under .double() in a test) still gets a
+    gradient of its own dtype, as autograd requires"""
+    x = torch.randn(9, 32, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(16, 32, dtype=torch.float64, requires_grad=True)
+    b = torch.zeros(16, dtype=torch.float64, requires_grad=True)
+    y = train_ops._LinearFunction.apply(x, w, b, True)
+    assert y.dtype == torch.float32
+    y.sum().backward()
+    assert x.grad.dtype == w.grad.dtype == b.grad.dtype == torch.float64
