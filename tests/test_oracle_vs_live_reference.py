@@ -340,3 +340,68 @@ def test_package_loads_a_state_dict_saved_by_the_reference_module(ref, sx, synth
     assert not [k for k in res.missing_keys if not k.startswith("backbone_wrapper.image_preprocessing_net.")]
     for k in hot:
         assert torch.equal(idm.state_dict()[k], sd[k]), k
+
+
+class _ScriptedIdModule:
+    """what test_pose_estimation needs from the module: eval() and test_image() -- here returning scripted winners"""
+
+    def __init__(self, script):
+        self.script, self.calls = script, 0
+
+    def eval(self):
+        return self
+
+    def test_image(self, img, mask, ori, dirs, rgb, rays_to_output=100):
+        idx, vals, up = self.script[self.calls]
+        self.calls += 1
+        return idx, vals, torch.zeros(ori.shape[0]), up, torch.zeros(256, 0)
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_pose_tail_vs_reference_evaluation_loop(ref, oracle, seed):
+    """a14 (test.py:157-198) run live: winners with repeated origins (whole rows and single coordinates -- the elementwise
+    isin(assume_unique=True) quirk), rays pointing away from the centre, and a frame of parallel winners (NaN centre -> identity pose);
+    the pose the reference's loop reports per frame against oracle.pose_tail on the same winners"""
+    from collections import namedtuple
+    import numpy as np
+    test_mod = importlib.import_module("pose_estimation.test")
+    g = torch.Generator().manual_seed(seed)
+    n = 600
+    centre = torch.randn(3, generator=g) * 2
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    ori = centre - dirs * (torch.rand(n, 1, generator=g) * 3 + 0.5) + 0.02 * torch.randn(n, 3, generator=g)
+    flip = torch.rand(n, generator=g) < 0.15                  # rays that point away from the centre
+    dirs[flip] = -dirs[flip]
+    ori[10:14] = ori[9]                                       # five rays share one origin (rows 9..13)
+    ori[20, 0] = ori[21, 0]                                   # a single repeated coordinate
+    ori[30, 1], ori[31, 2] = ori[32, 1], ori[32, 2]
+    script = []
+    for frame in range(4):
+        perm = torch.randperm(n, generator=g)[:100]
+        if frame == 1:
+            perm[:14] = torch.arange(5, 19)                   # make sure the shared origin is among the winners
+        if frame == 2:
+            perm[:6] = torch.tensor([20, 21, 30, 31, 32, 9])
+        vals = torch.rand(100, generator=g).sort(descending=True).values
+        script.append((perm, vals, torch.nn.functional.normalize(torch.randn(3, generator=g), dim=-1)))
+    # (below) a frame whose winners are all parallel to the z axis: det(R) = 0 exactly -> NaN centre -> identity pose
+    par_ori, par_dirs = ori.clone(), dirs.clone()
+    Cam = namedtuple("Cam", "uid R T FovY FovX image image_path image_name width height")
+    cams = [Cam(i, np.eye(3, dtype=np.float32), np.zeros(3, dtype=np.float32), np.float32(0.9), np.float32(0.9),
+                np.zeros((8, 8, 3), dtype=np.uint8), "", str(i), 8, 8) for i in range(len(script))]
+    res, *_ = test_mod.test_pose_estimation(cams, _ScriptedIdModule(script), ori, dirs, torch.zeros(n, 3),
+                                            torch.tensor([0.0, 0.0, 1.0]))
+    assert len(res) == len(script)
+    for frame, (idx, vals, up) in enumerate(script):
+        c2w, info = oracle.pose_tail(idx, vals, ori, dirs, up)
+        torch.testing.assert_close(c2w, torch.tensor(res[frame]["pred_c2w"]), rtol=1e-5, atol=1e-5, equal_nan=True)
+        if frame == 1:
+            assert int(info["weights"].numel()) < 100         # the shared origin did drop winners
+    par_dirs[:] = torch.tensor([0.0, 0.0, 1.0])
+    idx, vals, up = script[0]
+    res_p, *_ = test_mod.test_pose_estimation(cams[:1], _ScriptedIdModule([script[0]]), par_ori, par_dirs, torch.zeros(n, 3),
+                                              torch.tensor([0.0, 0.0, 1.0]))
+    c2w_p, _ = oracle.pose_tail(idx, vals, par_ori, par_dirs, up)
+    want = torch.tensor(res_p[0]["pred_c2w"])
+    assert torch.equal(want, torch.eye(4))  # NaN centre -> "wrong c2w" -> the identity pose (test.py:215-217)
+    assert torch.equal(c2w_p, want)
