@@ -405,3 +405,56 @@ def test_pose_tail_vs_reference_evaluation_loop(ref, oracle, seed):
     want = torch.tensor(res_p[0]["pred_c2w"])
     assert torch.equal(want, torch.eye(4))  # NaN centre -> "wrong c2w" -> the identity pose (test.py:215-217)
     assert torch.equal(c2w_p, want)
+
+
+@pytest.mark.parametrize("seed", SEEDS[:2])
+def test_package_evaluation_loop_vs_reference_loop(ref, oracle, sx, monkeypatch, seed):
+    """evaluate.test_pose_estimation against the reference's test_pose_estimation (test.py:23-323) run live on the same
+    cameras (RGB and RGBA images, real extrinsics) and the same scripted winners: every field of the result dicts and the
+    two averages.  The fused pose-tail launch is replaced by the oracle with the kernel's aux layout (aux[6] = rays kept
+    by the dedup, csrc/pose.cu) -- the loop around it is what is compared."""
+    from collections import namedtuple
+    import numpy as np
+    test_mod = importlib.import_module("pose_estimation.test")
+    evaluate = importlib.import_module("6dgs_b200.evaluate")
+
+    def pose_tail(ori, dirs, idx, weights, up):
+        c2w, info = oracle.pose_tail(idx, weights, ori, dirs, up)
+        aux = torch.zeros(8)
+        aux[6] = float(info["weights"].numel())
+        return c2w, aux
+
+    monkeypatch.setattr(evaluate.ops, "pose_tail", pose_tail)
+    g = torch.Generator().manual_seed(seed)
+    n = 500
+    centre = torch.randn(3, generator=g) * 2
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    ori = centre - dirs * (torch.rand(n, 1, generator=g) * 3 + 0.5) + 0.02 * torch.randn(n, 3, generator=g)
+    ori[10:13] = ori[9]
+    script, cams = [], []
+    Cam = namedtuple("Cam", "uid R T FovY FovX image image_path image_name width height")
+    for i in range(3):
+        perm = torch.randperm(n, generator=g)[:100]
+        if i == 1:
+            perm[:6] = torch.arange(8, 14)
+        script.append((perm, torch.rand(100, generator=g).sort(descending=True).values,
+                       torch.nn.functional.normalize(torch.randn(3, generator=g), dim=-1)))
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        R = (q * torch.sign(torch.linalg.det(q))).numpy().astype(np.float32)
+        T = (torch.randn(3, generator=g) * 2).numpy().astype(np.float32)
+        img = (torch.rand(12, 16, 4 if i == 1 else 3, generator=g) * 255).to(torch.uint8).numpy()
+        cams.append(Cam(i, R, T, np.float32(0.8), np.float32(1.0), img, "", str(i), 16, 12))
+    up = torch.tensor([0.0, 0.0, 1.0])
+    want, wt, wa, wl, wr = test_mod.test_pose_estimation(cams, _ScriptedIdModule(script), ori, dirs, torch.zeros(n, 3), up,
+                                                         sequence_id="s1", category_id="c1")
+    got, gt_, ga, gl, gr = evaluate.test_pose_estimation(cams, _ScriptedIdModule(script), ori, dirs, torch.zeros(n, 3), up,
+                                                         sequence_id="s1", category_id="c1")
+    assert len(got) == len(want) == 3
+    for a, b in zip(got, want):
+        assert set(a) == set(b)
+        for key in ("sequence_id", "category_name", "frame_id", "scores_loss", "recall", "total_optimization_time_in_ms"):
+            assert a[key] == b[key], key
+        assert abs(a["loss"] - b["loss"]) < 1e-6 * b["loss"]
+        torch.testing.assert_close(torch.tensor(a["pred_c2w"]), torch.tensor(b["pred_c2w"]), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(torch.tensor(a["gt_c2w"]), torch.tensor(b["gt_c2w"]), rtol=1e-6, atol=1e-6)
+    assert abs(gt_ - wt) < 1e-5 and abs(ga - wa) < 1e-3 and gl == wl == -1.0 and gr == wr == -1.0
