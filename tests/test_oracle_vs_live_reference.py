@@ -345,8 +345,10 @@ def test_package_loads_a_state_dict_saved_by_the_reference_module(ref, sx, synth
 class _ScriptedIdModule:
     """what test_pose_estimation needs from the module: eval() and test_image() -- here returning scripted winners"""
 
-    def __init__(self, script):
-        self.script, self.calls = script, 0
+    def __init__(self, script, scores=None):
+        import types
+        self.script, self.calls, self.scores = script, 0, scores
+        self.backbone_wrapper = types.SimpleNamespace(backbone_wh=(16, 16))
 
     def eval(self):
         return self
@@ -354,7 +356,8 @@ class _ScriptedIdModule:
     def test_image(self, img, mask, ori, dirs, rgb, rays_to_output=100):
         idx, vals, up = self.script[self.calls]
         self.calls += 1
-        return idx, vals, torch.zeros(ori.shape[0]), up, torch.zeros(256, 0)
+        scores = torch.zeros(ori.shape[0]) if self.scores is None else self.scores
+        return idx, vals, scores, up, torch.zeros(256, 0)
 
 
 @pytest.mark.parametrize("seed", SEEDS)
@@ -458,3 +461,17 @@ def test_package_evaluation_loop_vs_reference_loop(ref, oracle, sx, monkeypatch,
         torch.testing.assert_close(torch.tensor(a["pred_c2w"]), torch.tensor(b["pred_c2w"]), rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(torch.tensor(a["gt_c2w"]), torch.tensor(b["gt_c2w"]), rtol=1e-6, atol=1e-6)
     assert abs(gt_ - wt) < 1e-5 and abs(ga - wa) < 1e-3 and gl == wl == -1.0 and gr == wr == -1.0
+    # the "oracle rays" pass (test.py:110-142): score loss, recall of the scripted winners, poses from the TARGET scores
+    pred = torch.rand(n, generator=g) * 0.3
+    loss_r = importlib.import_module("pose_estimation.distance_based_loss").DistanceBasedScoreLoss()
+    want, wt, wa, wl, wr = test_mod.test_pose_estimation(cams, _ScriptedIdModule(script, pred), ori, dirs, torch.zeros(n, 3),
+                                                         up, loss_fn=loss_r)
+    got, gt_, ga, gl, gr = evaluate.test_pose_estimation(cams, _ScriptedIdModule(script, pred), ori, dirs, torch.zeros(n, 3),
+                                                         up, loss_fn=sx.DistanceBasedScoreLoss())
+    def same(x, y):  # a camera that sees no ray in front of it gives 0 / 0 targets upstream: NaN on both sides
+        return (x != x and y != y) or abs(x - y) <= 1e-5 * abs(y)
+
+    for a, b in zip(got, want):
+        assert same(a["scores_loss"], b["scores_loss"]) and a["recall"] == b["recall"]
+        torch.testing.assert_close(torch.tensor(a["pred_c2w"]), torch.tensor(b["pred_c2w"]), rtol=1e-4, atol=1e-4)
+    assert same(gl, wl) and gr == wr and abs(gt_ - wt) < 1e-4
