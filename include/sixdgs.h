@@ -137,7 +137,9 @@ int sixdgs_ray_features_x2(const float* ori, const float* dir, const float* rgb,
                            float* absmax, void* workspace, size_t workspace_bytes, void* stream);
 
 /* generic y[m,n] = act(x[m,k] w[n,k]^T + b[n]); k % 16 == 0, lda/ldc in elements (used for q_proj,
- * our_multihead_attention.py:74, with img features padded 398 -> 400). */
+ * our_multihead_attention.py:74, with img features padded 398 -> 400; for the dk / dq products of the score backward;
+ * and, in training mode, for the forward, dx and dW products of the ray MLP and the two projections -- the autograd of
+ * ray_preprocessor.py:36-46 / our_multihead_attention.py:74-75 under train.py:146-176, see 6dgs_b200/train_ops.py). */
 int sixdgs_linear(const float* x, int64_t m, int k, int lda, const float* w, const float* b, int n,
                   float* y, int ldc, int relu, void* stream);
 
